@@ -1,0 +1,32 @@
+"""audio_diffusion_pytorch on B200: the reference's public names (reference __init__.py:1-20)
+for the UNetV0 + VDiffusion/VSampler hot path, executed by hand-written sm_100a kernels.
+
+Out-of-scope names of the reference raise on use instead of silently
+running something else."""
+from .components import AppendChannelsPlugin, MelSpectrogram, UNetV0
+from .diffusion import (Diffusion, Distribution, LinearSchedule, Sampler, Schedule,
+                        UniformDistribution, VDiffusion, VSampler)
+from .models import DiffusionModel, DiffusionUpsampler, DiffusionVocoder
+from .unet import B200UNet
+
+
+def _out_of_scope(name: str, why: str):
+    class _Missing:
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"{name} is outside the B200 hot path this package "
+                                      f"replaces ({why}); use the reference implementation")
+    _Missing.__name__ = name
+    return _Missing
+
+
+XUNet = B200UNet
+LTPlugin = _out_of_scope("LTPlugin", "not used by any model class or config")
+VInpainter = _out_of_scope("VInpainter", "SURVEY.md 8f item 1")
+DiffusionAE = _out_of_scope("DiffusionAE", "needs the external audio_encoders_pytorch package")
+DiffusionAR = _out_of_scope("DiffusionAR", "use_modulation=False / SkipCat path, SURVEY.md 8f item 1")
+EncoderBase = _out_of_scope("EncoderBase", "DiffusionAE only")
+
+__all__ = ["UNetV0", "XUNet", "LTPlugin", "MelSpectrogram", "VDiffusion", "VSampler", "VInpainter",
+           "LinearSchedule", "UniformDistribution", "Diffusion", "Distribution", "Sampler",
+           "Schedule", "DiffusionModel", "DiffusionUpsampler", "DiffusionVocoder", "DiffusionAE",
+           "DiffusionAR", "EncoderBase", "AppendChannelsPlugin", "B200UNet"]

@@ -1,0 +1,441 @@
+// Bandwidth-bound row/elementwise kernels (CUDA cores): GroupNorm apply + SiLU, GroupNorm
+// statistics, LayerNorm over channels + FiLM (a_unet Modulation), the small conditioning
+// linears, NumberEmbedder features and the stand-alone VSampler update.
+// All activations are channels-last bf16, moved as 16-byte vectors (8 channels).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace adp {
+
+constexpr int kMaxC = 2048;
+
+// --------------------------------------------------------------------------- gn_silu
+// y = silu(x * a[b,c] + d[b,c]),  a = gamma*rstd, d = beta - mean*a  from (sum, sumsq).
+__global__ void __launch_bounds__(256)
+gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
+               const float* __restrict__ gamma, const float* __restrict__ beta, int T, int C,
+               int groups, float eps) {
+  __shared__ float s_a[kMaxC];
+  __shared__ float s_d[kMaxC];
+  const int b = blockIdx.y;
+  const int gsz = C / groups;
+  const double inv_n = 1.0 / (static_cast<double>(gsz) * T);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gsz;
+    const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
+    const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float a = gamma[c] * rstd;
+    s_a[c] = a;
+    s_d[c] = beta[c] - static_cast<float>(mean) * a;
+  }
+  __syncthreads();
+  const int vpr = C >> 3;  // vectors per row
+  const size_t nvec = static_cast<size_t>(T) * vpr;
+  const uint4* xb = x + static_cast<size_t>(b) * nvec;
+  uint4* yb = y + static_cast<size_t>(b) * nvec;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % vpr) << 3;
+    const uint4 u = __ldg(xb + i);
+    const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16(in[j]);
+      const float v0 = silu_f(f.x * s_a[c + 2 * j] + s_d[c + 2 * j]);
+      const float v1 = silu_f(f.y * s_a[c + 2 * j + 1] + s_d[c + 2 * j + 1]);
+      o[j] = pack_bf16(v0, v1);
+    }
+    yb[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// -------------------------------------------------------------------------- gn_stats
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int T, int C,
+                int groups) {
+  // each thread keeps a fixed channel-vector (stride is a multiple of vectors-per-row)
+  __shared__ float s_acc[2 * 64];
+  const int b = blockIdx.y;
+  const int gsz = C / groups;
+  const int vpr = C >> 3;
+  if (threadIdx.x < 2 * groups) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const size_t nvec = static_cast<size_t>(T) * vpr;
+  const uint4* xb = x + static_cast<size_t>(b) * nvec;
+  // make the per-thread stride a multiple of vpr so its channels never change
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t stride = (nthreads + vpr - 1) / vpr * vpr;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (tid < stride) {
+    for (size_t i = tid; i < nvec; i += stride) {
+      const uint4 u = __ldg(xb + i);
+      const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(in[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+    const int c = static_cast<int>(tid % vpr) << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / gsz;
+      atomicAdd(&s_acc[2 * g], s[j]);
+      atomicAdd(&s_acc[2 * g + 1], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * groups)
+    atomicAdd(stats + static_cast<size_t>(b) * 2 * groups + threadIdx.x,
+              static_cast<double>(s_acc[threadIdx.x]));
+}
+
+// --------------------------------------------------------------------------- ln_film
+// One row = C channels = C/8 vectors spread over LPR lanes (VPL vectors per lane).
+template <int VPL, bool PER_CH>
+__global__ void __launch_bounds__(256)
+ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ ss,
+               int ss_stride, double* __restrict__ stats, int T, int C, int lpr, int groups,
+               float eps) {
+  __shared__ float s_acc[2 * 64];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int rpw = 32 / lpr;          // rows per warp per iteration
+  const int sub = lane / lpr;        // which of those rows
+  const int l = lane - sub * lpr;    // lane inside the row
+  const int vpr = C >> 3;
+  const int gsz = groups > 0 ? C / groups : C;
+  const bool do_stats = stats != nullptr;
+  if (threadIdx.x < 128) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  // FiLM coefficients of this lane's channels (fixed for the whole kernel)
+  float fs[VPL][8], ft[VPL][8];
+#pragma unroll
+  for (int it = 0; it < VPL; ++it) {
+    const int c = (it * lpr + l) << 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      fs[it][j] = ss ? 1.f + ss[static_cast<size_t>(b) * ss_stride + c + j] : 1.f;
+      ft[it][j] = ss ? ss[static_cast<size_t>(b) * ss_stride + C + c + j] : 0.f;
+    }
+  }
+  constexpr int NACC = PER_CH ? 8 : VPL;
+  float as[NACC], aq[NACC];
+#pragma unroll
+  for (int j = 0; j < NACC; ++j) { as[j] = 0.f; aq[j] = 0.f; }
+
+  const uint4* xb = x + static_cast<size_t>(b) * T * vpr;
+  uint4* yb = y + static_cast<size_t>(b) * T * vpr;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / static_cast<float>(C);
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * rpw; base < T;
+       base += warps_total * rpw) {
+    const int row = base + sub;
+    const bool ok = row < T;
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < VPL; ++it) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (ok) u = __ldg(xb + static_cast<size_t>(row) * vpr + it * lpr + l);
+      const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(in[j]);
+        v[it][2 * j] = f.x; v[it][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+    for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int it = 0; it < VPL; ++it)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean; sq += d * d; }
+    for (int o = lpr >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+#pragma unroll
+    for (int it = 0; it < VPL; ++it) {
+      uint32_t o4[4];
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float y0 = (v[it][2 * j] - mean) * rstd * fs[it][2 * j] + ft[it][2 * j];
+        const float y1 = (v[it][2 * j + 1] - mean) * rstd * fs[it][2 * j + 1] + ft[it][2 * j + 1];
+        o4[j] = pack_bf16(y0, y1);
+        const float2 rr = unpack_bf16(o4[j]);   // statistics of what is stored
+        r[2 * j] = rr.x; r[2 * j + 1] = rr.y;
+      }
+      if (ok) {
+        yb[static_cast<size_t>(row) * vpr + it * lpr + l] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        if (do_stats) {
+          if constexpr (PER_CH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { as[j] += r[j]; aq[j] += r[j] * r[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { as[it] += r[j]; aq[it] += r[j] * r[j]; }
+          }
+        }
+      }
+    }
+  }
+  if (do_stats) {
+    if constexpr (PER_CH) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = ((l << 3) + j) / gsz;
+        atomicAdd(&s_acc[2 * g], as[j]);
+        atomicAdd(&s_acc[2 * g + 1], aq[j]);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < VPL; ++it) {
+        const int g = ((it * lpr + l) << 3) / gsz;
+        atomicAdd(&s_acc[2 * g], as[it]);
+        atomicAdd(&s_acc[2 * g + 1], aq[it]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * groups)
+      atomicAdd(stats + static_cast<size_t>(b) * 2 * groups + threadIdx.x,
+                static_cast<double>(s_acc[threadIdx.x]));
+  }
+}
+
+// --------------------------------------------------------------------- skinny_linear
+// y[b][n] = out_act(sum_k in_act(x[b][k]) * w[n][k] + bias[n]); 16 batch rows per CTA in smem,
+// one warp per output column, 16-value butterfly reduction.
+constexpr int kSkinnyRows = 16;
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ADP_ACT_GELU) return gelu_erf_f(v);
+  if (act == ADP_ACT_SILU) return silu_f(v);
+  return v;
+}
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                     const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
+                     int ldx, int ldw, int ldy, int in_act, int out_act) {
+  extern __shared__ float s_x[];  // [16][K]
+  const int b0 = blockIdx.y * kSkinnyRows;
+  for (int i = threadIdx.x; i < kSkinnyRows * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    float v = 0.f;
+    if (b0 + r < B) v = apply_act(x[static_cast<size_t>(b0 + r) * ldx + k], in_act);
+    s_x[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int kvecs = K >> 3;
+  for (int n = blockIdx.x * (blockDim.x >> 5) + warp; n < N; n += nwarps) {
+    float acc[kSkinnyRows];
+#pragma unroll
+    for (int r = 0; r < kSkinnyRows; ++r) acc[r] = 0.f;
+    const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<size_t>(n) * ldw);
+    for (int kv = lane; kv < kvecs; kv += 32) {
+      const uint4 u = __ldg(wr + kv);
+      const float2 w0 = unpack_bf16(u.x), w1 = unpack_bf16(u.y);
+      const float2 w2 = unpack_bf16(u.z), w3 = unpack_bf16(u.w);
+#pragma unroll
+      for (int r = 0; r < kSkinnyRows; ++r) {
+        const float4 xa = *reinterpret_cast<const float4*>(s_x + r * K + (kv << 3));
+        const float4 xb = *reinterpret_cast<const float4*>(s_x + r * K + (kv << 3) + 4);
+        acc[r] += xa.x * w0.x + xa.y * w0.y + xa.z * w1.x + xa.w * w1.y + xb.x * w2.x +
+                  xb.y * w2.y + xb.z * w3.x + xb.w * w3.y;
+      }
+    }
+    // butterfly: after offsets 16,8,4,2 each lane holds one of the 16 row sums
+#pragma unroll
+    for (int off = 16, cnt = kSkinnyRows; off >= 2; off >>= 1) {
+      cnt >>= 1;
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < cnt; ++j) {
+        const float send = hi ? acc[j] : acc[j + cnt];
+        const float keep = hi ? acc[j + cnt] : acc[j];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    const int r = ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) +
+                  ((lane & 2) ? 1 : 0);
+    if ((lane & 1) == 0 && b0 + r < B) {
+      float v = acc[0] + (bias ? bias[n] : 0.f);
+      y[static_cast<size_t>(b0 + r) * ldy + n] = apply_act(v, out_act);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------- time_features
+__global__ void time_features_kernel(const float* __restrict__ sigma,
+                                     const float* __restrict__ freqs, float* __restrict__ out,
+                                     int B, int nfreq, int ld_out) {
+  const int b = blockIdx.x;
+  const float s = sigma[b];
+  for (int j = threadIdx.x; j < ld_out; j += blockDim.x) {
+    float v = 0.f;
+    if (j == 0) v = s;
+    else if (j <= nfreq) v = sinf(s * freqs[j - 1] * 2.f * 3.14159265358979323846f);
+    else if (j <= 2 * nfreq) v = cosf(s * freqs[j - 1 - nfreq] * 2.f * 3.14159265358979323846f);
+    out[static_cast<size_t>(b) * ld_out + j] = v;
+  }
+}
+
+// ----------------------------------------------------------------------- sampler_step
+__global__ void sampler_step_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                    const float* __restrict__ ab, float* __restrict__ xn,
+                                    int64_t n) {
+  const float a0 = ab[0], b0 = ab[1], a1 = ab[2], b1 = ab[3];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float xv = x[i], vv = v[i];
+    const float x_pred = a0 * xv - b0 * vv;   // reference diffusion.py:185
+    const float n_pred = b0 * xv + a0 * vv;   // :186
+    xn[i] = a1 * x_pred + b1 * n_pred;        // :187
+  }
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                 int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(silu_f(x[i]));
+}
+
+static int pick_grid(size_t work_items, int per_block, int cap) {
+  size_t g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  return static_cast<int>(g);
+}
+
+}  // namespace adp
+
+using namespace adp;
+
+extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const float* gamma,
+                           const float* beta, int32_t B, int32_t T, int32_t C, int32_t groups,
+                           float eps, adp_stream_t stream) {
+  ADP_CHECK(x && y && stats && gamma && beta, "adp_gn_silu: null pointer");
+  ADP_CHECK(C % 8 == 0 && C <= kMaxC && groups > 0 && C % groups == 0,
+            "adp_gn_silu: C=%d groups=%d unsupported", C, groups);
+  const size_t nvec = static_cast<size_t>(T) * (C / 8);
+  dim3 grid(pick_grid(nvec, 256 * 4, 148 * 16 / (B < 16 ? B : 16) + 1), B);
+  gn_silu_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta, T, C, groups, eps);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_gn_stats(const void* x, double* stats, int32_t B, int32_t T, int32_t C,
+                            int32_t groups, adp_stream_t stream) {
+  ADP_CHECK(x && stats, "adp_gn_stats: null pointer");
+  ADP_CHECK(C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0,
+            "adp_gn_stats: C=%d groups=%d unsupported", C, groups);
+  const size_t nvec = static_cast<size_t>(T) * (C / 8);
+  dim3 grid(pick_grid(nvec, 256 * 8, 148 * 8 / (B < 8 ? B : 8) + 1), B);
+  gn_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), stats, T, C,
+                                                       groups);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_ln_film(const void* x, void* y, const float* scale_shift, int32_t ss_stride,
+                           double* stats_out, int32_t B, int32_t T, int32_t C, int32_t groups,
+                           float eps, adp_stream_t stream) {
+  ADP_CHECK(x && y, "adp_ln_film: null pointer");
+  ADP_CHECK(C % 8 == 0, "adp_ln_film: C=%d must be a multiple of 8", C);
+  const int vpr = C / 8;
+  int lpr, vpl;
+  if (vpr <= 32) {
+    ADP_CHECK((vpr & (vpr - 1)) == 0, "adp_ln_film: C/8=%d must be a power of two (<=32)", vpr);
+    lpr = vpr; vpl = 1;
+  } else {
+    ADP_CHECK(vpr % 32 == 0 && vpr / 32 <= 4, "adp_ln_film: C=%d unsupported (need C%%256==0, "
+              "C<=1024)", C);
+    lpr = 32; vpl = vpr / 32;
+  }
+  bool per_ch = false;
+  if (stats_out) {
+    ADP_CHECK(groups > 0 && groups <= 64 && C % groups == 0, "adp_ln_film: groups=%d", groups);
+    const int gsz = C / groups;
+    per_ch = gsz < 8;
+    ADP_CHECK(per_ch ? (vpl == 1) : (gsz % 8 == 0), "adp_ln_film: group size %d unsupported", gsz);
+  }
+  const int rows_per_block = 8 * (32 / lpr);
+  dim3 grid(pick_grid(T, rows_per_block * 4, 148 * 8 / (B < 8 ? B : 8) + 1), B);
+  const uint4* xi = static_cast<const uint4*>(x);
+  uint4* yo = static_cast<uint4*>(y);
+  cudaStream_t s = as_stream(stream);
+#define ADP_LN(VPL, PC)                                                                         \
+  ln_film_kernel<VPL, PC><<<grid, 256, 0, s>>>(xi, yo, scale_shift, ss_stride, stats_out, T, C, \
+                                               lpr, groups, eps)
+  if (per_ch) ADP_LN(1, true);
+  else if (vpl == 1) ADP_LN(1, false);
+  else if (vpl == 2) ADP_LN(2, false);
+  else if (vpl == 3) ADP_LN(3, false);
+  else ADP_LN(4, false);
+#undef ADP_LN
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_skinny_linear(const float* x, const void* w, const float* bias, float* y,
+                                 int32_t B, int32_t K, int32_t N, int32_t ldx, int32_t ldw,
+                                 int32_t ldy, int32_t in_act, int32_t out_act,
+                                 adp_stream_t stream) {
+  ADP_CHECK(x && w && y, "adp_skinny_linear: null pointer");
+  ADP_CHECK(K % 8 == 0 && ldw % 8 == 0 && K <= 3072 && K <= ldx && K <= ldw,
+            "adp_skinny_linear: K=%d ldx=%d ldw=%d unsupported", K, ldx, ldw);
+  const size_t smem = static_cast<size_t>(kSkinnyRows) * K * sizeof(float);
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    ADP_CUDA(cudaFuncSetAttribute(skinny_linear_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  dim3 grid(pick_grid(N, 8, 148 * 2), (B + kSkinnyRows - 1) / kSkinnyRows);
+  skinny_linear_kernel<<<grid, 256, smem, as_stream(stream)>>>(
+      x, static_cast<const __nv_bfloat16*>(w), bias, y, B, K, N, ldx, ldw, ldy, in_act, out_act);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_time_features(const float* sigma, const float* freqs, float* out, int32_t B,
+                                 int32_t nfreq, int32_t ld_out, adp_stream_t stream) {
+  ADP_CHECK(sigma && freqs && out && ld_out >= 2 * nfreq + 1, "adp_time_features: bad args");
+  time_features_kernel<<<B, 128, 0, as_stream(stream)>>>(sigma, freqs, out, B, nfreq, ld_out);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t stream) {
+  ADP_CHECK(x && y && n > 0, "adp_silu_bf16: bad args");
+  silu_bf16_kernel<<<pick_grid(static_cast<size_t>(n), 256, 148 * 4), 256, 0, as_stream(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_next,
+                                int64_t n, adp_stream_t stream) {
+  ADP_CHECK(x && v && ab && x_next && n > 0, "adp_sampler_step: bad args");
+  sampler_step_kernel<<<pick_grid(static_cast<size_t>(n), 256 * 4, 148 * 8), 256, 0,
+                        as_stream(stream)>>>(x, v, ab, x_next, n);
+  ADP_LAUNCH_CHECK();
+  return 0;
+}

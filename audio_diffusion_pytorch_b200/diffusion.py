@@ -1,0 +1,147 @@
+"""`diffusion_t` / `sampler_t` plugin slots (reference diffusion.py), B200-native.
+
+VDiffusion and VSampler keep the reference constructors and call signatures
+(reference diffusion.py:68-95, :158-190).  When the wrapped net is the B200 U-Net the
+per-step arithmetic is fused into the net's last kernel and the loop launches one CUDA
+graph per step; with any other `net` the same algebra runs as the generic fused
+`adp_sampler_step` kernel after the net call.
+"""
+from math import pi
+from typing import Any, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+from tqdm import tqdm
+
+from . import ops
+from .unet import B200UNet
+
+
+class Distribution:
+    """Interface used by different distributions (reference diffusion.py:16-20)."""
+
+    def __call__(self, num_samples: int, device: torch.device):
+        raise NotImplementedError()
+
+
+class UniformDistribution(Distribution):
+    """reference diffusion.py:23-30"""
+
+    def __init__(self, vmin: float = 0.0, vmax: float = 1.0):
+        super().__init__()
+        self.vmin, self.vmax = vmin, vmax
+
+    def __call__(self, num_samples: int, device: torch.device = torch.device("cpu")):
+        return (self.vmax - self.vmin) * torch.rand(num_samples, device=device) + self.vmin
+
+
+class Diffusion(nn.Module):
+    """Interface used by different diffusion methods"""
+
+
+class Schedule(nn.Module):
+    """Interface used by different sampling schedules (reference diffusion.py:135-139)."""
+
+    def forward(self, num_steps: int, device: torch.device) -> Tensor:
+        raise NotImplementedError()
+
+
+class LinearSchedule(Schedule):
+    """reference diffusion.py:142-148"""
+
+    def __init__(self, start: float = 1.0, end: float = 0.0):
+        super().__init__()
+        self.start, self.end = start, end
+
+    def forward(self, num_steps: int, device: Any) -> Tensor:
+        return torch.linspace(self.start, self.end, num_steps, device=device)
+
+
+class Sampler(nn.Module):
+    pass
+
+
+def _alpha_beta(sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+    angle = sigmas * pi / 2          # reference diffusion.py:77-80
+    return torch.cos(angle), torch.sin(angle)
+
+
+def _inner_b200(net: nn.Module) -> Optional[B200UNet]:
+    return net if isinstance(net, B200UNet) else None
+
+
+class VDiffusion(Diffusion):
+    """v-objective diffusion loss (reference diffusion.py:68-95).
+
+    RNG contract kept: `sigma_distribution(B)` is drawn first, then `randn_like(x)`, both on
+    x.device.  With the B200 net the noising (`alpha*x + beta*noise`) is fused into the first
+    kernel and the MSE against `alpha*noise - beta*x` into the last."""
+
+    def __init__(self, net: nn.Module, sigma_distribution: Distribution = UniformDistribution(),
+                 loss_fn: Any = F.mse_loss):
+        super().__init__()
+        self.net = net
+        self.sigma_distribution = sigma_distribution
+        self.loss_fn = loss_fn
+
+    def get_alpha_beta(self, sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+        return _alpha_beta(sigmas)
+
+    def forward(self, x: Tensor, **kwargs) -> Tensor:
+        batch_size, device = x.shape[0], x.device
+        sigmas = self.sigma_distribution(num_samples=batch_size, device=device)   # :85
+        noise = torch.randn_like(x)                                               # :88
+        net = _inner_b200(self.net)
+        if net is not None and self.loss_fn is F.mse_loss:
+            from .training import fused_v_loss
+            return fused_v_loss(net, x, noise, sigmas, **kwargs)
+        sig_b = sigmas.view(-1, *([1] * (x.ndim - 1)))
+        alphas, betas = _alpha_beta(sig_b)
+        x_noisy = alphas * x + betas * noise                                      # :91
+        v_target = alphas * noise - betas * x                                     # :92
+        v_pred = self.net(x_noisy, sigmas, **kwargs)                              # :94
+        return self.loss_fn(v_pred, v_target)                                     # :95
+
+
+class VSampler(Sampler):
+    """reference diffusion.py:158-190"""
+
+    diffusion_types = [VDiffusion]
+
+    def __init__(self, net: nn.Module, schedule: Schedule = LinearSchedule()):
+        super().__init__()
+        self.net = net
+        self.schedule = schedule
+
+    def get_alpha_beta(self, sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+        return _alpha_beta(sigmas)
+
+    @torch.no_grad()
+    def forward(self, x_noisy: Tensor, num_steps: int, show_progress: bool = False,
+                **kwargs) -> Tensor:
+        b = x_noisy.shape[0]
+        sigmas_1d = self.schedule(num_steps + 1, device=x_noisy.device)           # :177
+        sigmas = sigmas_1d[:, None].expand(-1, b)                                 # :178
+        alphas, betas = _alpha_beta(sigmas_1d)                                    # :180
+        # the bar shows the schedule value from a host copy made once, before the loop
+        # (the reference formats a device scalar every step = one sync per step, :188)
+        host_sig = sigmas_1d.tolist() if show_progress else None
+        bar = tqdm(range(num_steps), disable=not show_progress)
+
+        def progress():
+            for i in bar:
+                yield i
+                if host_sig is not None:
+                    bar.set_description(f"Sampling (noise={host_sig[i + 1]:.2f})")
+
+        net = _inner_b200(self.net)
+        if net is not None:
+            return net.sample_loop(x_noisy, sigmas, alphas, betas, progress=progress(), **kwargs)
+        ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], 1).float().contiguous()
+        x = x_noisy.float().contiguous().clone()
+        for i in progress():
+            v = self.net(x, sigmas[i], **kwargs).float().contiguous()             # :184
+            ops.sampler_step(x, v, ab[i], x)                                      # :185-187
+        return x.to(x_noisy.dtype)

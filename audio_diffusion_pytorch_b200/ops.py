@@ -1,0 +1,209 @@
+"""Tensor-facing wrappers over the C ABI (one Python call = one kernel launch on the current
+CUDA stream) and the host-side weight packers for adp_conv_gemm.
+
+Activations are channels-last bf16 [B, T, C]; statistics fp64 [B, G, 2]; conditioning fp32.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ConvGemmArgs, NarrowConvArgs, StemInArgs, StemOutArgs
+
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_check() -> None:
+    _lib.check(_lib.lib().adp_device_check(), "adp_device_check")
+
+
+# ------------------------------------------------------------------------------ packers
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def _pad_rows(w2d: Tensor, n_pad: int) -> Tensor:
+    out = torch.zeros(n_pad, w2d.shape[1], dtype=torch.bfloat16, device=w2d.device)
+    out[: w2d.shape[0]] = w2d.to(torch.bfloat16)
+    return out.contiguous()
+
+
+def pack_conv(w: Tensor) -> Tensor:
+    """Conv1d weight [co, ci, k] -> [n_pad, k*ci] (tap-major K), rows zero-padded to 16.
+    Serves k=3 p=1 convs (taps -1,0,+1) and k=s=f downsample convs (1 tap over the
+    [B, T/f, f*ci] view of the channels-last input)."""
+    co, ci, k = w.shape
+    return _pad_rows(w.permute(0, 2, 1).reshape(co, k * ci), round_up(co, 16))
+
+
+def pack_linear(w: Tensor) -> Tensor:
+    return _pad_rows(w, round_up(w.shape[0], 16))
+
+
+def pack_upsample_conv(w: Tensor, f: int) -> Tensor:
+    """nn.Upsample(nearest, f) -> Conv1d(k=3, p=1) folded into f output phases on the
+    LOW-RES input: phase 0 = {W0 @ x[q-1], (W1+W2) @ x[q]}, phase f-1 = {(W0+W1) @ x[q],
+    W2 @ x[q+1]}, interior phases = {(W0+W1+W2) @ x[q]}.  -> [f*n_pad, 2*ci]."""
+    co, ci, k = w.shape
+    assert k == 3 and f >= 2
+    n_pad = round_up(co, 16)
+    w = w.float()
+    w0, w1, w2 = w[:, :, 0], w[:, :, 1], w[:, :, 2]
+    out = torch.zeros(f, n_pad, 2 * ci, dtype=torch.float32, device=w.device)
+    for p in range(f):
+        if p == 0:
+            out[p, :co, :ci], out[p, :co, ci:] = w0, w1 + w2
+        elif p == f - 1:
+            out[p, :co, :ci], out[p, :co, ci:] = w0 + w1, w2
+        else:
+            out[p, :co, :ci] = w0 + w1 + w2
+    return out.reshape(f * n_pad, 2 * ci).to(torch.bfloat16).contiguous()
+
+
+# ---------------------------------------------------------------------------------- ops
+def conv_gemm(a: Tensor, w: Tensor, out: Tensor, *, c_in: int, n_valid: int,
+              taps: Sequence[int] = (0,), up_factor: int = 0, bias: Optional[Tensor] = None,
+              residual: Optional[Tensor] = None, gate: Optional[Tensor] = None,
+              stats: Optional[Tensor] = None, groups: int = 8, block_n: int = 0) -> Tensor:
+    """a: bf16 [B, T, lda]; w: packed bf16 [phases*n_pad, k_total]; out: [B, T, ldo]."""
+    B, T, lda = a.shape
+    phases = up_factor if up_factor > 1 else 1
+    args = ConvGemmArgs()
+    args.a, args.w, args.out = a.data_ptr(), w.data_ptr(), out.data_ptr()
+    args.bias, args.residual, args.gate, args.stats = _p(bias), _p(residual), _p(gate), _p(stats)
+    args.B, args.T, args.c_in, args.lda, args.ldo = B, T, c_in, lda, out.shape[-1]
+    args.k_total = w.shape[1]
+    args.n_pad, args.n_valid, args.phases = w.shape[0] // phases, n_valid, phases
+    args.ntaps = len(taps)
+    for i in range(3):
+        args.tap_off[i] = taps[i] if i < len(taps) else 0
+    args.up_factor, args.groups, args.block_n = up_factor, groups, block_n
+    args.out_fp32 = 1 if out.dtype == torch.float32 else 0
+    args.ld_gate = 0 if gate is None else gate.stride(0)
+    _lib.check(_lib.lib().adp_conv_gemm(C.byref(args), _stream()), "adp_conv_gemm")
+    return out
+
+
+def gn_silu(x: Tensor, y: Tensor, stats: Tensor, gamma: Tensor, beta: Tensor, groups: int,
+            eps: float = 1e-5) -> Tensor:
+    B, T, Cc = x.shape
+    _lib.check(_lib.lib().adp_gn_silu(x.data_ptr(), y.data_ptr(), stats.data_ptr(),
+                                      gamma.data_ptr(), beta.data_ptr(), B, T, Cc, groups, eps,
+                                      _stream()), "adp_gn_silu")
+    return y
+
+
+def gn_stats(x: Tensor, stats: Tensor, groups: int) -> Tensor:
+    B, T, Cc = x.shape
+    _lib.check(_lib.lib().adp_gn_stats(x.data_ptr(), stats.data_ptr(), B, T, Cc, groups,
+                                       _stream()), "adp_gn_stats")
+    return stats
+
+
+def ln_film(x: Tensor, y: Tensor, scale_shift: Optional[Tensor] = None, ss_stride: int = 0,
+            stats_out: Optional[Tensor] = None, groups: int = 8, eps: float = 1e-6) -> Tensor:
+    B, T, Cc = x.shape
+    _lib.check(_lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
+                                      _p(stats_out), B, T, Cc, groups, eps, _stream()),
+               "adp_ln_film")
+    return y
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: float) -> Tensor:
+    """q: bf16 view [B, Tq, >=heads*64] (row pitch = stride(1)); k, v over Tk rows."""
+    B, Tq = q.shape[0], q.shape[1]
+    Tk = k.shape[1]
+    _lib.check(_lib.lib().adp_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B,
+                                        heads, Tq, Tk, q.stride(1), k.stride(1), v.stride(1),
+                                        o.stride(1), scale, _stream()), "adp_attention")
+    return o
+
+
+def skinny_linear(x: Tensor, w: Tensor, bias: Optional[Tensor], y: Tensor, K: int, N: int,
+                  in_act: int = ACT_NONE, out_act: int = ACT_NONE) -> Tensor:
+    _lib.check(_lib.lib().adp_skinny_linear(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(),
+                                            x.shape[0], K, N, x.stride(0), w.stride(0),
+                                            y.stride(0), in_act, out_act, _stream()),
+               "adp_skinny_linear")
+    return y
+
+
+def time_features(sigma: Tensor, freqs: Tensor, out: Tensor) -> Tensor:
+    _lib.check(_lib.lib().adp_time_features(sigma.data_ptr(), freqs.data_ptr(), out.data_ptr(),
+                                            sigma.shape[0], freqs.shape[0], out.stride(0),
+                                            _stream()), "adp_time_features")
+    return out
+
+
+def stem_in(x: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, f: int, *,
+            append: Optional[Tensor] = None, noise: Optional[Tensor] = None,
+            alpha: Optional[Tensor] = None, beta: Optional[Tensor] = None,
+            stats: Optional[Tensor] = None, groups: int = 8) -> Tensor:
+    a = StemInArgs()
+    a.x, a.append, a.noise, a.alpha, a.beta = x.data_ptr(), _p(append), _p(noise), _p(alpha), _p(beta)
+    a.w, a.bias, a.out, a.stats = w.data_ptr(), _p(bias), out.data_ptr(), _p(stats)
+    a.B, a.cx, a.T = x.shape
+    a.ca = 0 if append is None else append.shape[1]
+    a.c0, a.f, a.groups = w.shape[0], f, groups
+    _lib.check(_lib.lib().adp_stem_in(C.byref(a), _stream()), "adp_stem_in")
+    return out
+
+
+def stem_out(h: Tensor, x: Tensor, w: Tensor, bias: Optional[Tensor], gate: Tensor, f: int, *,
+             append: Optional[Tensor] = None, w_adapt: Optional[Tensor] = None,
+             b_adapt: Optional[Tensor] = None, v_out: Optional[Tensor] = None,
+             x_next: Optional[Tensor] = None, ab: Optional[Tensor] = None,
+             noise: Optional[Tensor] = None, alpha: Optional[Tensor] = None,
+             beta: Optional[Tensor] = None, loss_sum: Optional[Tensor] = None,
+             dv: Optional[Tensor] = None, cfg_scale: Optional[float] = None) -> None:
+    a = StemOutArgs()
+    a.h, a.x, a.append, a.w, a.bias = h.data_ptr(), x.data_ptr(), _p(append), w.data_ptr(), _p(bias)
+    a.w_adapt, a.b_adapt, a.gate = _p(w_adapt), _p(b_adapt), gate.data_ptr()
+    a.v_out, a.x_next, a.ab = _p(v_out), _p(x_next), _p(ab)
+    a.noise, a.alpha, a.beta, a.loss_sum, a.dv = _p(noise), _p(alpha), _p(beta), _p(loss_sum), _p(dv)
+    a.cfg = 0 if cfg_scale is None else 1
+    a.cfg_scale = 1.0 if cfg_scale is None else cfg_scale
+    a.B, a.cx, a.T = x.shape
+    a.ca = 0 if append is None else append.shape[1]
+    a.c0, a.co, a.f = h.shape[-1], w.shape[0], f
+    a.ld_gate = gate.stride(0)
+    _lib.check(_lib.lib().adp_stem_out(C.byref(a), _stream()), "adp_stem_out")
+
+
+def narrow_conv(x: Tensor, y: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, w: Tensor,
+                bias: Optional[Tensor], groups: int, *, residual: Optional[Tensor] = None,
+                scale_shift: Optional[Tensor] = None, ss_stride: int = 0,
+                stats_out: Optional[Tensor] = None, gn_eps: float = 1e-5,
+                ln_eps: float = 1e-6) -> Tensor:
+    a = NarrowConvArgs()
+    a.x, a.y, a.stats_in = x.data_ptr(), y.data_ptr(), stats_in.data_ptr()
+    a.gamma, a.beta, a.w, a.bias = gamma.data_ptr(), beta.data_ptr(), w.data_ptr(), _p(bias)
+    a.residual, a.scale_shift, a.stats_out = _p(residual), _p(scale_shift), _p(stats_out)
+    a.ss_stride = ss_stride
+    a.B, a.T, a.C = x.shape
+    a.groups, a.gn_eps, a.ln_eps = groups, gn_eps, ln_eps
+    _lib.check(_lib.lib().adp_narrow_conv(C.byref(a), _stream()), "adp_narrow_conv")
+    return y
+
+
+def silu_bf16(x: Tensor, y: Tensor) -> Tensor:
+    _lib.check(_lib.lib().adp_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()),
+               "adp_silu_bf16")
+    return y
+
+
+def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:
+    _lib.check(_lib.lib().adp_sampler_step(x.data_ptr(), v.data_ptr(), ab.data_ptr(),
+                                           x_next.data_ptr(), x.numel(), _stream()),
+               "adp_sampler_step")
+    return x_next

@@ -1,0 +1,688 @@
+"""UNetV0 on B200: the reference's `net_t` plugin slot (reference components.py:34-105),
+rebuilt over the sm_100a kernels of libadp_b200.so.
+
+`UNetV0(dim=1, in_channels=..., channels=[...], ...)` takes the reference's kwargs verbatim
+and returns an nn.Module with the reference's call signature
+
+    net(x[B,Cin,T], time[B], *, features=None, embedding=None, embedding_scale=1.0,
+        embedding_mask_proba=0.0, channels=None[, append_channels]) -> [B,Cout,T]
+
+Parameters keep PyTorch shapes (Conv1d [co,ci,k], Linear [out,in]) and are registered in
+the same order as the a_unet module tree, so `load_reference_parameters` copies a reference
+model's weights positionally.  The forward pass is a flat *program*: a list of kernel
+launches over pre-allocated channels-last bf16 buffers, captured into one CUDA graph per
+(batch, length) shape; nothing in it falls back to PyTorch ops or to the CPU.
+"""
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import ops
+
+
+def exists(v) -> bool:
+    return v is not None
+
+
+def default(v, d):
+    return v if exists(v) else d
+
+
+# ----------------------------------------------------------------------------- parameters
+class ResnetParams(nn.Module):
+    """a_unet ResnetBlock: (GroupNorm, SiLU, Conv1d k3) x 2 + identity shortcut."""
+
+    def __init__(self, channels: int, groups: int):
+        super().__init__()
+        self.gn1 = nn.GroupNorm(groups, channels)
+        self.conv1 = nn.Conv1d(channels, channels, 3, padding=1)
+        self.gn2 = nn.GroupNorm(groups, channels)
+        self.conv2 = nn.Conv1d(channels, channels, 3, padding=1)
+
+
+class ModulationParams(nn.Module):
+    """a_unet Modulation: Linear(SiLU(features)) -> (scale, shift); LayerNorm has no params."""
+
+    def __init__(self, channels: int, features: int):
+        super().__init__()
+        self.proj = nn.Linear(features, 2 * channels)
+
+
+class AttentionParams(nn.Module):
+    """a_unet Attention: norm, norm_context, to_q, to_kv, to_out (no biases)."""
+
+    def __init__(self, channels: int, head_features: int, heads: int,
+                 context_features: Optional[int] = None):
+        super().__init__()
+        mid = head_features * heads
+        ctx = default(context_features, channels)
+        self.norm = nn.LayerNorm(channels)
+        self.norm_context = nn.LayerNorm(ctx)
+        self.to_q = nn.Linear(channels, mid, bias=False)
+        self.to_kv = nn.Linear(ctx, 2 * mid, bias=False)
+        self.to_out = nn.Linear(mid, channels, bias=False)
+
+
+class ItemParams(nn.Module):
+    """One repetition of [ResnetItem, ModulationItem, AttentionItem?, CrossAttentionItem?]."""
+
+    def __init__(self, channels: int, groups: int, features: int, att: bool, cross: bool,
+                 head_features: Optional[int], heads: Optional[int],
+                 embedding_features: Optional[int]):
+        super().__init__()
+        self.resnet = ResnetParams(channels, groups)
+        self.modulation = ModulationParams(channels, features)
+        self.attention = AttentionParams(channels, head_features, heads) if att else None
+        self.cross = (AttentionParams(channels, head_features, heads, embedding_features)
+                      if cross else None)
+
+
+class LevelParams(nn.Module):
+    """a_unet Block: registration order = skip_adapter, (down, items, inner, items_up, up), merge."""
+
+    def __init__(self, in_ch: int, out_ch: int, ch: int, factor: int, n_items: int, inner,
+                 **item_kw):
+        super().__init__()
+        self.adapter = nn.Conv1d(in_ch, out_ch, 1) if in_ch != out_ch else None
+        self.down = nn.Conv1d(in_ch, ch, factor, stride=factor)
+        self.items_down = nn.ModuleList([ItemParams(ch, **item_kw) for _ in range(n_items)])
+        self.inner = inner
+        self.items_up = nn.ModuleList([ItemParams(ch, **item_kw) for _ in range(n_items)])
+        self.up = nn.Conv1d(ch, out_ch, 3, padding=1)
+        self.merge = nn.Linear(item_kw["features"], out_ch)
+        self.in_ch, self.out_ch, self.ch, self.factor = in_ch, out_ch, ch, factor
+
+
+class TimeParams(nn.Module):
+    """a_unet TimeConditioningPlugin: NumberEmbedder + (Linear, GELU) applied twice (shared)."""
+
+    def __init__(self, features: int, dim: int = 256):
+        super().__init__()
+        self.weights = nn.Parameter(torch.randn(dim // 2))
+        self.to_out = nn.Linear(dim + 1, features)
+        self.mlp = nn.Linear(features, features)
+
+
+# -------------------------------------------------------------------------------- program
+class _Pool:
+    """Reuses activation buffers whose value is dead (better L2 residency than fresh ones)."""
+
+    def __init__(self, device, reuse: bool):
+        self.device, self.reuse = device, reuse
+        self.free: Dict[Tuple, List[Tensor]] = {}
+        self.total_bytes = 0
+
+    def get(self, *shape, dtype=torch.bfloat16) -> Tensor:
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if self.reuse and lst:
+            return lst.pop()
+        t = torch.empty(*shape, dtype=dtype, device=self.device)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t: Optional[Tensor]) -> None:
+        if t is not None and self.reuse:
+            self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class _Plan:
+    """Everything tied to one input shape: static I/O buffers, workspaces, the launch list and
+    (after warm-up) its CUDA graph."""
+
+    def __init__(self):
+        self.prog: List[Callable[[], None]] = []
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.n_launches = 0
+        self.runs = 0
+
+    def add(self, fn: Callable[[], None]) -> None:
+        self.prog.append(fn)
+        self.n_launches += 1
+
+    def run_eager(self) -> None:
+        for fn in self.prog:
+            fn()
+
+
+class B200UNet(nn.Module):
+    """See module docstring.  Reference parity notes per block are in include/adp_b200.h."""
+
+    GN_EPS = 1e-5      # nn.GroupNorm default (a_unet ConvBlock)
+    ATT_LN_EPS = 1e-5  # nn.LayerNorm default (a_unet Attention norms)
+    MOD_LN_EPS = 1e-6  # a_unet Modulation LayerNorm
+
+    def __init__(self, dim: int, in_channels: int, channels: Sequence[int],
+                 factors: Sequence[int], items: Sequence[int],
+                 attentions: Optional[Sequence[int]] = None,
+                 cross_attentions: Optional[Sequence[int]] = None,
+                 context_channels: Optional[Sequence[int]] = None,
+                 attention_features: Optional[int] = None,
+                 attention_heads: Optional[int] = None,
+                 embedding_features: Optional[int] = None, resnet_groups: int = 8,
+                 use_modulation: bool = True, modulation_features: int = 1024,
+                 embedding_max_length: Optional[int] = None,
+                 use_time_conditioning: bool = True, use_embedding_cfg: bool = False,
+                 use_text_conditioning: bool = False, out_channels: Optional[int] = None,
+                 append_channels: int = 0):
+        super().__init__()
+        n = len(channels)
+        attentions = default(attentions, [0] * n)
+        cross_attentions = default(cross_attentions, [0] * n)
+        context_channels = default(context_channels, [0] * n)
+        xs = (channels, factors, items, attentions, cross_attentions, context_channels)
+        assert all(len(x) == n for x in xs)                       # reference components.py:61
+        assert dim == 1, "the B200 path implements the 1-D (waveform) U-Net"
+        if use_embedding_cfg:                                     # components.py:66-68
+            assert exists(embedding_max_length), "use_embedding_cfg requires embedding_max_length"
+        if use_time_conditioning:                                 # components.py:75
+            assert use_modulation, "use_time_conditioning requires use_modulation=True"
+        if use_text_conditioning:
+            raise NotImplementedError(
+                "use_text_conditioning builds a T5 encoder (a_unet TextConditioningPlugin); pass "
+                "precomputed `embedding=` with use_text_conditioning=False (SURVEY.md 3.4)")
+        if not use_modulation:
+            raise NotImplementedError("use_modulation=False (SkipCat) is outside the B200 hot path")
+        if any(c > 0 for c in context_channels):
+            raise NotImplementedError("context_channels / InjectChannelsItem is outside the hot path")
+        if any(attentions) or any(cross_attentions):
+            assert exists(attention_features) and exists(attention_heads), \
+                "AttentionItem requires attention_features and attention_heads"
+            assert attention_features == 64, "the tcgen05 attention kernel is built for head dim 64"
+        if any(cross_attentions):
+            assert exists(embedding_features), "CrossAttentionItem requires embedding_features"
+
+        self.x_channels = in_channels - append_channels   # channels of `x` (rest is appended)
+        self.append_channels = append_channels
+        self.in_channels, self.out_channels = in_channels, default(out_channels, in_channels)
+        self.channels, self.factors, self.items = list(channels), list(factors), list(items)
+        self.attentions, self.cross_attentions = list(attentions), list(cross_attentions)
+        self.groups, self.features = resnet_groups, modulation_features
+        self.heads, self.head_features = attention_heads, attention_features
+        self.embedding_features = embedding_features
+        self.use_time_conditioning, self.use_embedding_cfg = use_time_conditioning, use_embedding_cfg
+        for c in self.channels:
+            assert c % resnet_groups == 0 and c % 8 == 0, "channels must be multiples of 8 and groups"
+        assert self.out_channels <= 4 and self.in_channels <= 8, "stem kernels: in<=8, out<=4 channels"
+
+        # registration order mirrors a_unet: time plugin, cfg plugin, then the recursive blocks
+        self.time = TimeParams(modulation_features) if use_time_conditioning else None
+        self.fixed_embedding = (nn.Embedding(embedding_max_length, embedding_features)
+                                if use_embedding_cfg else None)
+
+        def build(i: int):
+            if i == n:
+                return None
+            in_ch = in_channels if i == 0 else channels[i - 1]
+            out_ch = self.out_channels if i == 0 else in_ch
+            return LevelParams(in_ch, out_ch, channels[i], factors[i], items[i], build(i + 1),
+                               groups=resnet_groups, features=modulation_features,
+                               att=bool(attentions[i]), cross=bool(cross_attentions[i]),
+                               head_features=attention_features, heads=attention_heads,
+                               embedding_features=embedding_features)
+
+        self.net = build(0)
+        self._plans: Dict[Tuple, _Plan] = {}
+        self._packed = None
+        self._packed_version = None
+        self.use_cuda_graph = True
+
+    # ------------------------------------------------------------------ weights
+    def levels(self) -> List[LevelParams]:
+        out, lvl = [], self.net
+        while lvl is not None:
+            out.append(lvl)
+            lvl = lvl.inner
+        return out
+
+    @torch.no_grad()
+    def load_reference_parameters(self, reference_net: nn.Module) -> None:
+        """Positional copy from a reference UNetV0 (same kwargs): both trees register
+        parameters in a_unet order, so shapes must line up one to one."""
+        src, dst = list(reference_net.parameters()), list(self.parameters())
+        assert len(src) == len(dst), f"parameter count {len(src)} != {len(dst)}"
+        for s, d in zip(src, dst):
+            assert s.shape == d.shape, f"shape mismatch {tuple(s.shape)} vs {tuple(d.shape)}"
+            d.copy_(s)
+        self._packed = None
+
+    def _version(self) -> int:
+        return sum(p._version for p in self.parameters())
+
+    @torch.no_grad()
+    def packed(self):
+        """Kernel-layout copies of the weights (bf16 GEMM operands, folded LayerNorm affines,
+        one concatenated conditioning projection).  Rebuilt when a parameter changes."""
+        v = self._version()
+        if self._packed is not None and self._packed_version == v:
+            return self._packed
+        P: Dict = {}
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        cond_w, cond_b, off = [], [], 0
+
+        def add_cond(lin: nn.Linear) -> int:
+            nonlocal off
+            n_out = lin.weight.shape[0]
+            pad = ops.round_up(n_out, 8)
+            w = torch.zeros(pad, lin.weight.shape[1], device=lin.weight.device)
+            b = torch.zeros(pad, device=lin.weight.device)
+            w[:n_out], b[:n_out] = lin.weight.detach().float(), lin.bias.detach().float()
+            cond_w.append(w)
+            cond_b.append(b)
+            start, off = off, off + pad
+            return start
+
+        def pack_att(a: AttentionParams, self_attn: bool) -> Dict:
+            wq = a.to_q.weight.detach().float()
+            wkv = a.to_kv.weight.detach().float()
+            g1, b1 = a.norm.weight.detach().float(), a.norm.bias.detach().float()
+            g2, b2 = a.norm_context.weight.detach().float(), a.norm_context.bias.detach().float()
+            d: Dict = {"w_out": ops.pack_linear(a.to_out.weight.detach())}
+            # LayerNorm affine folded into the projection: W (xhat*g + b) = (W*g) xhat + W b
+            wq_f, bq = wq * g1[None, :], wq @ b1
+            wkv_f, bkv = wkv * g2[None, :], wkv @ b2
+            if self_attn:
+                d["w_qkv"] = ops.pack_linear(torch.cat([wq_f, wkv_f], 0))
+                d["b_qkv"] = torch.cat([bq, bkv]).contiguous()
+            else:
+                d["w_q"], d["b_q"] = ops.pack_linear(wq_f), bq.contiguous()
+                d["w_kv"], d["b_kv"] = ops.pack_linear(wkv_f), bkv.contiguous()
+            return d
+
+        def pack_item(it: ItemParams, narrow: bool) -> Dict:
+            r = it.resnet
+            d: Dict = {"gn1": (f32(r.gn1.weight), f32(r.gn1.bias)),
+                       "gn2": (f32(r.gn2.weight), f32(r.gn2.bias)),
+                       "b1": f32(r.conv1.bias), "b2": f32(r.conv2.bias),
+                       "ss_off": add_cond(it.modulation.proj)}
+            if narrow:
+                d["w1"], d["w2"] = f32(r.conv1.weight), f32(r.conv2.weight)
+            else:
+                d["w1"], d["w2"] = ops.pack_conv(r.conv1.weight.detach()), ops.pack_conv(r.conv2.weight.detach())
+            if it.attention is not None:
+                d["att"] = pack_att(it.attention, True)
+            if it.cross is not None:
+                d["cross"] = pack_att(it.cross, False)
+            return d
+
+        P["levels"] = []
+        for i, lvl in enumerate(self.levels()):
+            narrow = lvl.ch == 8
+            L: Dict = {"down_b": f32(lvl.down.bias), "up_b": f32(lvl.up.bias)}
+            if i == 0:
+                L["down_w"], L["up_w"] = f32(lvl.down.weight), f32(lvl.up.weight)
+                if lvl.adapter is not None:
+                    L["adapt_w"] = f32(lvl.adapter.weight[:, :, 0])
+                    L["adapt_b"] = f32(lvl.adapter.bias)
+            else:
+                L["down_w"] = ops.pack_conv(lvl.down.weight.detach())
+                L["up_w"] = (ops.pack_upsample_conv(lvl.up.weight.detach(), lvl.factor)
+                             if lvl.factor > 1 else ops.pack_conv(lvl.up.weight.detach()))
+            L["items_down"] = [pack_item(it, narrow) for it in lvl.items_down]
+            L["items_up"] = [pack_item(it, narrow) for it in lvl.items_up]
+            L["gate_off"] = add_cond(lvl.merge)
+            P["levels"].append(L)
+        n_tot = off
+        w_all = torch.cat(cond_w, 0)
+        n_pad = ops.round_up(n_tot, 256)
+        w_pad = torch.zeros(n_pad, w_all.shape[1], dtype=torch.bfloat16, device=w_all.device)
+        w_pad[:n_tot] = w_all.to(torch.bfloat16)
+        P["cond_w"], P["cond_b"], P["cond_n"] = w_pad.contiguous(), torch.cat(cond_b).contiguous(), n_tot
+        if self.time is not None:
+            t = self.time
+            kdim = t.to_out.weight.shape[1]
+            kpad = ops.round_up(kdim, 8)
+            w_emb = torch.zeros(self.features, kpad, dtype=torch.bfloat16, device=w_all.device)
+            w_emb[:, :kdim] = t.to_out.weight.detach().to(torch.bfloat16)
+            P["time"] = {"freqs": f32(t.weights), "w_emb": w_emb.contiguous(), "b_emb": f32(t.to_out.bias),
+                         "w_mlp": t.mlp.weight.detach().to(torch.bfloat16).contiguous(),
+                         "b_mlp": f32(t.mlp.bias), "kpad": kpad}
+        self._packed, self._packed_version = P, v
+        return P
+
+    # --------------------------------------------------------------------- plan
+    def _build_plan(self, B: int, T: int, Bh: int, M: int, mode: str) -> _Plan:
+        """B = batch of x; Bh = rows the trunk runs (2B under classifier-free guidance);
+        M = embedding tokens (0 if none); mode in {'v', 'sample'}."""
+        dev = self.net.down.weight.device
+        P = self.packed()
+        plan = _Plan()
+        pool = _Pool(dev, reuse=True)
+        G, Fm = self.groups, self.features
+        levels = self.levels()
+        total_f = 1
+        for lv in levels:
+            total_f *= lv.factor
+        assert T % total_f == 0, f"length {T} must be divisible by the product of factors {total_f}"
+
+        # ---- static I/O
+        plan.x = torch.zeros(B, self.x_channels, T, device=dev)
+        plan.append = torch.zeros(B, self.append_channels, T, device=dev) if self.append_channels else None
+        plan.sigma = torch.zeros(Bh, device=dev)
+        plan.features_in = torch.zeros(Bh, Fm, device=dev)
+        plan.v = torch.zeros(B, self.out_channels, T, device=dev)
+        plan.ab = torch.zeros(4, device=dev)
+        plan.embedding = torch.zeros(Bh, M, self.embedding_features, dtype=torch.bfloat16,
+                                     device=dev) if M else None
+        plan.cfg_scale = None
+
+        # ---- statistics arena (zeroed once per forward)
+        n_slots = 2 + sum(2 * (len(lv.items_down) + len(lv.items_up)) + 3 for lv in levels)
+        arena = torch.zeros(n_slots, Bh, G, 2, dtype=torch.float64, device=dev)
+        slot_i = [0]
+
+        def new_stats() -> Tensor:
+            s = arena[slot_i[0]]
+            slot_i[0] += 1
+            return s
+
+        plan.add(lambda: arena.zero_())
+
+        # ---- conditioning: f = MLP(GELU(embed(sigma))) (+features); ss = W_all SiLU(f) + b
+        n_tot = P["cond_n"]
+        ss_all = torch.zeros(Bh, ops.round_up(n_tot, 8), device=dev)
+        cond_bf = torch.zeros(1, Bh, Fm, dtype=torch.bfloat16, device=dev)
+        fvec = torch.zeros(Bh, Fm, device=dev)
+        plan.use_features_in = False
+        if self.time is not None:
+            tp = P["time"]
+            feat = torch.zeros(Bh, tp["kpad"], device=dev)
+            e0, e1 = torch.zeros(Bh, Fm, device=dev), torch.zeros(Bh, Fm, device=dev)
+            plan.add(lambda: ops.time_features(plan.sigma, tp["freqs"], feat))
+            plan.add(lambda: ops.skinny_linear(feat, tp["w_emb"], tp["b_emb"], e0, tp["kpad"], Fm,
+                                               out_act=ops.ACT_GELU))
+            plan.add(lambda: ops.skinny_linear(e0, tp["w_mlp"], tp["b_mlp"], e1, Fm, Fm,
+                                               out_act=ops.ACT_GELU))
+            plan.add(lambda: ops.skinny_linear(e1, tp["w_mlp"], tp["b_mlp"], fvec, Fm, Fm,
+                                               out_act=ops.ACT_GELU))
+
+            def add_features():
+                if plan.use_features_in:
+                    fvec.add_(plan.features_in)
+            plan.add(add_features)
+        else:
+            plan.add(lambda: fvec.copy_(plan.features_in))
+        plan.add(lambda: ops.silu_bf16(fvec, cond_bf))
+        cond_bias = _pad_to(P["cond_b"], ss_all.shape[1])
+        plan.add(lambda: ops.conv_gemm(cond_bf, P["cond_w"], ss_all.view(1, Bh, -1), c_in=Fm,
+                                       n_valid=ss_all.shape[1], bias=cond_bias))
+        ss_stride = ss_all.shape[1]
+
+        # ---- one item chain
+        def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], lv: LevelParams, Tl: int,
+                      last_needs_stats: bool) -> Tuple[Tensor, Optional[Tensor]]:
+            C = lv.ch
+            narrow = C == 8
+            for idx, ip in enumerate(items_p):
+                ss = ss_all[:, ip["ss_off"]:]
+                has_att, has_cross = "att" in ip, "cross" in ip
+                item_last = idx == len(items_p) - 1
+                want_stats = (not item_last) or last_needs_stats
+                mod_stats = new_stats() if (want_stats and not (has_att or has_cross)) else None
+                h_stats = new_stats()
+                if narrow:
+                    h = pool.get(Bh, Tl, C)
+                    y = pool.get(Bh, Tl, C)
+                    plan.add(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.narrow_conv(
+                        x, h, s, ip["gn1"][0], ip["gn1"][1], ip["w1"], ip["b1"], G, stats_out=hs,
+                        gn_eps=self.GN_EPS))
+                    plan.add(lambda x=x, h=h, y=y, hs=h_stats, ms=mod_stats, ip=ip, ss=ss: ops.narrow_conv(
+                        h, y, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], ip["b2"], G, residual=x,
+                        scale_shift=ss, ss_stride=ss_stride, stats_out=ms, gn_eps=self.GN_EPS,
+                        ln_eps=self.MOD_LN_EPS))
+                    pool.put(h)
+                else:
+                    a = pool.get(Bh, Tl, C)
+                    h = pool.get(Bh, Tl, C)
+                    r = pool.get(Bh, Tl, C)
+                    y = pool.get(Bh, Tl, C)
+                    plan.add(lambda x=x, a=a, s=x_stats, ip=ip: ops.gn_silu(
+                        x, a, s, ip["gn1"][0], ip["gn1"][1], G, self.GN_EPS))
+                    plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.conv_gemm(
+                        a, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs,
+                        groups=G))
+                    plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.gn_silu(
+                        h, a, hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS))
+                    plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
+                        a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
+                    plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats: ops.ln_film(
+                        r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS))
+                    pool.put(a)
+                    pool.put(h)
+                    pool.put(r)
+                # the item's input is dead now (a level's skip is the chain's *output*)
+                pool.put(x)
+                x, x_stats = y, mod_stats
+                mid = (self.heads or 0) * 64
+                for kind in ("att", "cross"):
+                    if kind not in ip:
+                        continue
+                    ap = ip[kind]
+                    is_last_att = kind == "cross" or not has_cross
+                    out_stats = new_stats() if (want_stats and is_last_att) else None
+                    xn = pool.get(Bh, Tl, C)
+                    o = pool.get(Bh, Tl, mid)
+                    y2 = pool.get(Bh, Tl, C)
+                    plan.add(lambda x=x, xn=xn: ops.ln_film(x, xn, None, 0, None, G, self.ATT_LN_EPS))
+                    if kind == "att":
+                        qkv = pool.get(Bh, Tl, 3 * mid)
+                        plan.add(lambda xn=xn, qkv=qkv, ap=ap: ops.conv_gemm(
+                            xn, ap["w_qkv"], qkv, c_in=C, n_valid=3 * mid, bias=ap["b_qkv"]))
+                        plan.add(lambda qkv=qkv, o=o: ops.attention(
+                            qkv[..., :mid], qkv[..., mid:2 * mid], qkv[..., 2 * mid:], o, self.heads,
+                            64 ** -0.5))
+                        pool.put(qkv)
+                    else:
+                        E = self.embedding_features
+                        q = pool.get(Bh, Tl, mid)
+                        en = pool.get(Bh, M, E)
+                        kv = pool.get(Bh, M, 2 * mid)
+                        plan.add(lambda en=en: ops.ln_film(plan.embedding, en, None, 0, None, G,
+                                                           self.ATT_LN_EPS))
+                        plan.add(lambda en=en, kv=kv, ap=ap: ops.conv_gemm(
+                            en, ap["w_kv"], kv, c_in=E, n_valid=2 * mid, bias=ap["b_kv"]))
+                        plan.add(lambda xn=xn, q=q, ap=ap: ops.conv_gemm(
+                            xn, ap["w_q"], q, c_in=C, n_valid=mid, bias=ap["b_q"]))
+                        plan.add(lambda q=q, kv=kv, o=o: ops.attention(
+                            q, kv[..., :mid], kv[..., mid:], o, self.heads, 64 ** -0.5))
+                        pool.put(q)
+                        pool.put(en)
+                        pool.put(kv)
+                    plan.add(lambda o=o, y2=y2, x=x, ap=ap, os_=out_stats: ops.conv_gemm(
+                        o, ap["w_out"], y2, c_in=mid, n_valid=C, residual=x, stats=os_, groups=G))
+                    pool.put(xn)
+                    pool.put(o)
+                    pool.put(x)
+                    x, x_stats = y2, out_stats
+            return x, x_stats
+
+        # ---- recursive level walk
+        def run_level(i: int, x_in: Optional[Tensor], T_in: int) -> Tuple[Tensor, Optional[Tensor]]:
+            """Returns the level's output [Bh, T_in, out_ch] (+ its stats) for i >= 1;
+            level 0 writes plan.v / x_next itself."""
+            lv, Lp = levels[i], P["levels"][i]
+            Tl = T_in // lv.factor
+            C = lv.ch
+            innermost = i == len(levels) - 1
+            x = pool.get(Bh, Tl, C)
+            st = new_stats()
+            if i == 0:
+                for half in range(Bh // B):
+                    plan.add(lambda half=half, x=x, st=st: ops.stem_in(
+                        plan.x, Lp["down_w"], Lp["down_b"], x[half * B:(half + 1) * B], lv.factor,
+                        append=plan.append, stats=st[half * B:(half + 1) * B], groups=G))
+            else:
+                plan.add(lambda x=x, st=st: ops.conv_gemm(
+                    x_in.view(Bh, Tl, lv.factor * lv.in_ch), Lp["down_w"], x, c_in=lv.factor * lv.in_ch,
+                    n_valid=C, bias=Lp["down_b"], stats=st, groups=G))
+            x, st = run_items(x, st, Lp["items_down"], lv, Tl, last_needs_stats=innermost)
+            if not innermost:
+                skip = x
+                x, st = run_level(i + 1, skip, Tl)
+                pool.put(skip)
+            x, st = run_items(x, st, Lp["items_up"], lv, Tl, last_needs_stats=False)
+            gate = ss_all[:, Lp["gate_off"]:]
+            if i == 0:
+                plan.h0 = x
+                plan.gate0 = gate
+                plan.level0 = (lv, Lp)
+                return x, None
+            out = pool.get(Bh, T_in, lv.out_ch)
+            ost = new_stats()
+            if lv.factor > 1:
+                plan.add(lambda x=x, out=out, ost=ost: ops.conv_gemm(
+                    x, Lp["up_w"], out.view(Bh, Tl, lv.factor * lv.out_ch), c_in=C, n_valid=lv.out_ch,
+                    up_factor=lv.factor, bias=Lp["up_b"], residual=x_in.view(Bh, Tl, lv.factor * lv.out_ch),
+                    gate=gate, stats=ost, groups=G))
+            else:
+                plan.add(lambda x=x, out=out, ost=ost: ops.conv_gemm(
+                    x, Lp["up_w"], out, c_in=C, n_valid=lv.out_ch, taps=(-1, 0, 1), bias=Lp["up_b"],
+                    residual=x_in, gate=gate, stats=ost, groups=G))
+            pool.put(x)
+            return out, ost
+
+        run_level(0, None, T)
+        lv0, L0 = plan.level0
+
+        def final():
+            kw = dict(append=plan.append, w_adapt=L0.get("adapt_w"), b_adapt=L0.get("adapt_b"),
+                      cfg_scale=plan.cfg_scale)
+            if mode == "sample":   # v and the VSampler update in one pass; x advanced in place
+                ops.stem_out(plan.h0, plan.x, L0["up_w"], L0["up_b"], plan.gate0, lv0.factor,
+                             x_next=plan.x, ab=plan.ab, **kw)
+            else:
+                ops.stem_out(plan.h0, plan.x, L0["up_w"], L0["up_b"], plan.gate0, lv0.factor,
+                             v_out=plan.v, **kw)
+        plan.add(final)
+        plan.workspace_bytes = pool.total_bytes
+        assert slot_i[0] <= n_slots
+        return plan
+
+    def _plan(self, B: int, T: int, Bh: int, M: int, mode: str, baked: Tuple = ()) -> _Plan:
+        """`baked` = host-side values frozen into the captured graph (cfg scale, features flag)."""
+        key = (B, T, Bh, M, mode, baked, self._version())
+        plan = self._plans.get(key)
+        if plan is None:
+            ops.device_check()
+            self._plans = {k: v for k, v in self._plans.items() if k[-1] == key[-1]}
+            plan = self._plans[key] = self._build_plan(B, T, Bh, M, mode)
+        return plan
+
+    def _execute(self, plan: _Plan) -> None:
+        """First call eager (validates every launch), second call captures, then replays."""
+        if not self.use_cuda_graph:
+            plan.run_eager()
+        elif plan.graph is not None:
+            plan.graph.replay()
+        elif plan.runs == 0:
+            plan.run_eager()
+        else:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                plan.run_eager()
+            plan.graph = g
+            g.replay()
+        plan.runs += 1
+
+    def _stage_inputs(self, plan: _Plan, x: Tensor, time: Optional[Tensor], features, embedding,
+                      embedding_scale: float, embedding_mask_proba: float, append_channels):
+        B = x.shape[0]
+        Bh = plan.sigma.shape[0]
+        cfg = Bh == 2 * B
+        if plan.x.data_ptr() != x.data_ptr():
+            plan.x.copy_(x)
+        if self.append_channels:
+            assert exists(append_channels), "append_channels is required (AppendChannelsPlugin)"
+            plan.append.copy_(append_channels)
+        if self.time is not None:
+            assert exists(time), "time conditioning requires the time argument"
+            plan.sigma[:B].copy_(time.reshape(-1))
+            if cfg:
+                plan.sigma[B:].copy_(time.reshape(-1))
+            plan.use_features_in = exists(features)
+        else:
+            assert exists(features), "use_time_conditioning=False needs features="
+        if exists(features):
+            plan.features_in[:B].copy_(features)
+            if cfg:
+                plan.features_in[B:].copy_(features)
+        if plan.embedding is not None:
+            assert exists(embedding), "ClassiferFreeGuidancePlugin requires embedding"
+            emb = embedding
+            if self.fixed_embedding is not None:
+                fixed = self.fixed_embedding.weight[: emb.shape[1]].unsqueeze(0).expand_as(emb)
+                if embedding_mask_proba > 0.0:          # a_unet CFG plugin, training-time masking
+                    mask = torch.bernoulli(torch.full((B, 1, 1), embedding_mask_proba,
+                                                      device=emb.device)).to(torch.bool)
+                    emb = torch.where(mask, fixed, emb)
+                if cfg:
+                    plan.embedding[B:].copy_(fixed)
+            plan.embedding[:B].copy_(emb)
+        plan.cfg_scale = float(embedding_scale) if cfg else None
+
+    def _shape_key(self, x: Tensor, embedding, embedding_scale: float):
+        B, _, T = x.shape
+        cfg = self.use_embedding_cfg and exists(embedding) and embedding_scale != 1.0
+        M = embedding.shape[1] if (exists(embedding) and any(self.cross_attentions)) else 0
+        return B, T, (2 * B if cfg else B), M
+
+    @torch.no_grad()
+    def forward(self, x: Tensor, time: Optional[Tensor] = None, *, features: Optional[Tensor] = None,
+                embedding: Optional[Tensor] = None, embedding_scale: float = 1.0,
+                embedding_mask_proba: float = 0.0, channels=None,
+                append_channels: Optional[Tensor] = None) -> Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            pass  # training goes through VDiffusion (fused loss + backward); plain forward is inference
+        assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+        assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
+        if self.use_embedding_cfg:
+            assert exists(embedding), "ClassiferFreeGuidancePlugin requires embedding"
+        B, T, Bh, M = self._shape_key(x, embedding, embedding_scale)
+        plan = self._plan(B, T, Bh, M, "v", (float(embedding_scale) if Bh != B else None,
+                                             exists(features)))
+        self._stage_inputs(plan, x.float(), time, features, embedding, embedding_scale,
+                           embedding_mask_proba, append_channels)
+        self._execute(plan)
+        return plan.v.clone().to(x.dtype)
+
+    @torch.no_grad()
+    def sample_loop(self, x_noisy: Tensor, sigmas: Tensor, alphas: Tensor, betas: Tensor,
+                    progress=None, **kwargs) -> Tensor:
+        """VSampler's loop (reference diffusion.py:183-188) with the per-step update fused into
+        the net's last kernel: one graph launch per step, no host sync inside the loop."""
+        assert x_noisy.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+        embedding = kwargs.get("embedding")
+        scale = kwargs.get("embedding_scale", 1.0)
+        B, T, Bh, M = self._shape_key(x_noisy, embedding, scale)
+        plan = self._plan(B, T, Bh, M, "sample", (float(scale) if Bh != B else None,
+                                                  exists(kwargs.get("features"))))
+        self._stage_inputs(plan, x_noisy.float(), sigmas[0], kwargs.get("features"), embedding, scale,
+                           kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"))
+        num_steps = sigmas.shape[0] - 1
+        ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], dim=1).float().contiguous()
+        sig = sigmas.float().repeat(1, Bh // B).contiguous()      # [N+1, Bh]
+        steps = range(num_steps) if progress is None else progress
+        for i in steps:   # two 16..64-byte device copies + one graph launch per step, no host sync
+            plan.ab.copy_(ab[i], non_blocking=True)
+            plan.sigma.copy_(sig[i], non_blocking=True)
+            self._execute(plan)
+        return plan.x.clone().to(x_noisy.dtype)
+
+
+def _pad_to(t: Tensor, n: int) -> Tensor:
+    if t.shape[0] == n:
+        return t
+    out = torch.zeros(n, dtype=t.dtype, device=t.device)
+    out[: t.shape[0]] = t
+    return out
+
+
+def UNetV0(dim: int, in_channels: int, channels: Sequence[int], factors: Sequence[int],
+           items: Sequence[int], **kwargs) -> nn.Module:
+    """Drop-in for reference components.py:34 `UNetV0` (same kwargs, asserts and call
+    signature); returns the B200-native module."""
+    return B200UNet(dim=dim, in_channels=in_channels, channels=channels, factors=factors,
+                    items=items, **kwargs)

@@ -1,0 +1,203 @@
+/* adp_b200.h -- C ABI of libadp_b200.so, the sm_100a (B200) kernels behind the
+ * audio_diffusion_pytorch hot path:  UNetV0 forward/backward + VDiffusion + VSampler.
+ *
+ * The reference (archinetai/audio-diffusion-pytorch) is pure Python and has no FFI; its
+ * boundary for this path is three nn.Module factories (net_t / diffusion_t / sampler_t,
+ * reference models.py:25-38).  Each entry point below replaces the arithmetic of one
+ * a_unet / diffusion.py building block that those modules execute; the block it replaces
+ * is cited per function (reference paths are relative to /root/reference/; "a_unet" =
+ * the un-vendored third-party package, behaviour per SURVEY.md appendix A).
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless stated.
+ *  - activations are channels-last bf16: x[b][t][c]  (the reference is [b][c][t] fp32;
+ *    the stem kernels convert at the network boundary).  fp32 for statistics/conditioning.
+ *  - the caller owns every buffer (incl. workspaces); no entry point allocates or
+ *    synchronises, all are CUDA-graph capturable on `stream` (a cudaStream_t).
+ *  - return 0 on success, non-zero on error; adp_last_error() describes the last error of
+ *    the calling thread.  There is NO CPU fallback: a non-sm_100 device is an error.
+ */
+#ifndef ADP_B200_H_
+#define ADP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* adp_stream_t; /* cudaStream_t */
+
+/* activation codes for adp_skinny_linear */
+enum { ADP_ACT_NONE = 0, ADP_ACT_GELU = 1, ADP_ACT_SILU = 2 };
+
+int adp_version(void);
+const char* adp_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200). */
+int adp_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * adp_conv_gemm: shifted-tap GEMM on tcgen05 tensor cores (TMA -> smem -> UMMA -> TMEM).
+ *   out[b,t, p*n_valid + n] = epi( sum_tap sum_k  a[b, t + off(p,tap), k] * w[p*n_pad + n, tap*c_in + k] )
+ * with rows outside [0,T) reading as zero (TMA out-of-bounds fill = the conv padding).
+ * Replaces (a_unet): ConvBlock's Conv1d k=3 p=1 (ResnetItem), Downsample Conv1d k=s=f (as a
+ * 1-tap GEMM over the [B,T/f,f*C] view), nn.Upsample(nearest,f)+Conv1d k=3 (up_factor=f:
+ * per output phase p the 3 taps collapse to <=2 taps on the low-res input, weights
+ * pre-summed by the caller), every nn.Linear of Attention (to_q/to_kv/to_out), and the
+ * 1x1 convs.  Epilogue: + bias[n]; * gate[b,n] (MergeModulate scale); + residual (ResnetBlock
+ * shortcut / attention skip / U-Net skip); optional per-(b,group) sum & sum-of-squares of the
+ * result (the next GroupNorm's statistics) accumulated into `stats`.
+ */
+typedef struct adp_conv_gemm_args {
+  const void* a;        /* bf16 [B][T][lda]                       */
+  const void* w;        /* bf16 [phases*n_pad][k_total], k_total = max_taps*c_in */
+  void* out;            /* bf16 [B][T][ldo]                       */
+  const float* bias;    /* fp32 [n_valid] or NULL                  */
+  const void* residual; /* bf16 [B][T][ldo] or NULL               */
+  const float* gate;    /* fp32 [B][ld_gate] (first n_valid used) or NULL */
+  double* stats;        /* fp64 [B][groups][2] (sum, sumsq) accumulated, or NULL */
+  int32_t B, T;
+  int32_t c_in;         /* K per tap; multiple of 16               */
+  int32_t lda, ldo;     /* row pitches in elements (multiples of 8) */
+  int32_t k_total;      /* row pitch of w in elements              */
+  int32_t n_pad;        /* padded outputs per phase (multiple of the N tile) */
+  int32_t n_valid;      /* real outputs per phase (multiple of 8)  */
+  int32_t phases;       /* 1, or up_factor                         */
+  int32_t ntaps;        /* taps when up_factor <= 1 (1..3)         */
+  int32_t tap_off[3];   /* row offset of each tap                  */
+  int32_t up_factor;    /* 0/1: plain; f>=2: nearest-upsample-by-f + conv3 phase decomposition */
+  int32_t groups;       /* GroupNorm groups for `stats` (n_valid % groups == 0) */
+  int32_t block_n;      /* N tile override (16..256), 0 = auto      */
+  int32_t out_fp32;     /* 1: `out` is fp32 [B][T][ldo] (conditioning projections); no residual */
+  int32_t ld_gate;      /* row pitch of gate in elements (multiple of 4); 0 = n_valid */
+} adp_conv_gemm_args;
+int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream);
+
+/* y = SiLU(GroupNorm(x)) -- a_unet ConvBlock's nn.GroupNorm(groups, C, eps) + nn.SiLU.
+ * stats: fp64 [B][groups][2] = (sum, sumsq) over the group's channels and all T. */
+int adp_gn_silu(const void* x, void* y, const double* stats, const float* gamma,
+                const float* beta, int32_t B, int32_t T, int32_t C, int32_t groups, float eps,
+                adp_stream_t stream);
+
+/* Per-(b,group) sum / sumsq of a channels-last bf16 tensor, accumulated into stats. */
+int adp_gn_stats(const void* x, double* stats, int32_t B, int32_t T, int32_t C, int32_t groups,
+                 adp_stream_t stream);
+
+/* y = LayerNorm_C(x; no affine, eps) * (1 + scale[b,c]) + shift[b,c]
+ * -- a_unet Modulation (ModulationItem); scale_shift fp32 [B][ss_stride] with scale at
+ * [0,C) and shift at [C,2C), or NULL for a plain LayerNorm (attention pre-norm; its affine
+ * is folded into the following projection by the caller).  stats_out as in adp_conv_gemm. */
+int adp_ln_film(const void* x, void* y, const float* scale_shift, int32_t ss_stride,
+                double* stats_out, int32_t B, int32_t T, int32_t C, int32_t groups, float eps,
+                adp_stream_t stream);
+
+/* o = softmax(q k^T * scale) v per (batch, head), head dim 64 -- a_unet AttentionBase.
+ * q: bf16 [B][Tq][ldq] (head h at columns [h*64,(h+1)*64)), k/v likewise over Tk rows,
+ * o: bf16 [B][Tq][ldo].  tcgen05 flash attention (S and O accumulators in TMEM). */
+int adp_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
+                  int32_t Tq, int32_t Tk, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo,
+                  float scale, adp_stream_t stream);
+
+/* y[b][n] = out_act( sum_k in_act(x[b][k]) * w[n][k] + bias[n] ),  B <= 64 rows.
+ * The step-conditioning linears: NumberEmbedder.to_out, TimeConditioningPlugin MLP,
+ * Modulation.to_scale_shift and MergeModulate.to_scale of every item (a_unet).
+ * x fp32 [B][ldx], w bf16 [N][ldw], y fp32 [B][ldy]. */
+int adp_skinny_linear(const float* x, const void* w, const float* bias, float* y, int32_t B,
+                      int32_t K, int32_t N, int32_t ldx, int32_t ldw, int32_t ldy,
+                      int32_t in_act, int32_t out_act, adp_stream_t stream);
+
+/* NumberEmbedder features: out[b] = [sigma_b, sin(2 pi sigma_b w_j), cos(2 pi sigma_b w_j), 0-pad]
+ * (a_unet NumberEmbedder.forward).  out fp32 [B][ld_out], ld_out >= 2*nfreq+1. */
+int adp_time_features(const float* sigma, const float* freqs, float* out, int32_t B,
+                      int32_t nfreq, int32_t ld_out, adp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Network boundary ("stem") kernels: fp32 [B][C][T] <-> bf16 channels-last.
+ *
+ * adp_stem_in: level-0 DownsampleItem Conv1d(cx+ca -> c0, k=s=f) on cat([x, append],1)
+ * (reference components.py:175 AppendChannelsPlugin + a_unet Downsample), optionally on the
+ * VDiffusion-noised input x_noisy = alpha_b*x + beta_b*noise (reference diffusion.py:91).
+ * Emits the GroupNorm statistics of its output. */
+typedef struct adp_stem_in_args {
+  const float* x;       /* fp32 [B][cx][T]                          */
+  const float* append;  /* fp32 [B][ca][T] or NULL                  */
+  const float* noise;   /* fp32 [B][cx][T] or NULL                  */
+  const float* alpha;   /* fp32 [B] (with noise)                    */
+  const float* beta;    /* fp32 [B]                                 */
+  const float* w;       /* fp32 [c0][cx+ca][f]  (PyTorch Conv1d layout) */
+  const float* bias;    /* fp32 [c0]                                */
+  void* out;            /* bf16 [B][T/f][c0]                        */
+  double* stats;        /* fp64 [B][groups][2] or NULL              */
+  int32_t B, T, cx, ca, c0, f, groups;
+} adp_stem_in_args;
+int adp_stem_in(const adp_stem_in_args* args, adp_stream_t stream);
+
+/* adp_stem_out: level-0 UpsampleItem (nearest f + Conv1d(c0 -> co, k=3, p=1)), SkipAdapter
+ * (1x1 conv on cat([x, append]) iff cx+ca != co), MergeModulate  v = skip + gate[b]*y
+ * (a_unet), then optionally, fused:
+ *   - classifier-free guidance  v = v_m + (v_c - v_m)*cfg_scale  (a_unet CFG plugin;
+ *     h holds 2B rows: conditional then masked),
+ *   - the VSampler update (reference diffusion.py:185-187) writing x_next,
+ *   - the VDiffusion loss partial sums of (v - (alpha*noise - beta*x))^2 (diffusion.py:92-95)
+ *     and d(loss)/dv. */
+typedef struct adp_stem_out_args {
+  const void* h;        /* bf16 [Bh][T/f][c0], Bh = B (or 2B with cfg) */
+  const float* x;       /* fp32 [B][cx][T]   (block input, the skip) */
+  const float* append;  /* fp32 [B][ca][T] or NULL                   */
+  const float* w;       /* fp32 [co][c0][3]                          */
+  const float* bias;    /* fp32 [co]                                 */
+  const float* w_adapt; /* fp32 [co][cx+ca] or NULL (identity skip)  */
+  const float* b_adapt; /* fp32 [co] or NULL                         */
+  const float* gate;    /* fp32 [Bh][ld_gate] (first co used)        */
+  float* v_out;         /* fp32 [B][co][T] or NULL                   */
+  /* sampler fusion */
+  float* x_next;        /* fp32 [B][co][T] or NULL                   */
+  const float* ab;      /* fp32 [4]: alpha_i, beta_i, alpha_{i+1}, beta_{i+1} (device) */
+  /* loss fusion */
+  const float* noise;   /* fp32 [B][co][T] or NULL                   */
+  const float* alpha;   /* fp32 [B]                                  */
+  const float* beta;    /* fp32 [B]                                  */
+  double* loss_sum;     /* fp64 [1] accumulated sum of squared error */
+  float* dv;            /* fp32 [B][co][T] = 2*(v - v_target)/numel, or NULL */
+  float cfg_scale;      /* used iff cfg != 0                         */
+  int32_t cfg;
+  int32_t B, T, cx, ca, c0, co, f;
+  int32_t ld_gate;      /* row pitch of gate; 0 = co                 */
+} adp_stem_out_args;
+int adp_stem_out(const adp_stem_out_args* args, adp_stream_t stream);
+
+/* ResnetItem ConvBlock for narrow levels (C == 8), CUDA cores, one pass:
+ *   y = Conv1d_k3(SiLU(GroupNorm(x))) + bias [+ residual]
+ * then optionally the following ModulationItem on the result (LayerNorm_C + FiLM),
+ * and the GroupNorm statistics of what is written.  (a_unet ConvBlock / ResnetBlock /
+ * Modulation; wide levels use adp_gn_silu + adp_conv_gemm + adp_ln_film.) */
+typedef struct adp_narrow_conv_args {
+  const void* x;            /* bf16 [B][T][C]                        */
+  void* y;                  /* bf16 [B][T][C]                        */
+  const double* stats_in;   /* fp64 [B][groups][2]                   */
+  const float* gamma;       /* fp32 [C]                              */
+  const float* beta;        /* fp32 [C]                              */
+  const float* w;           /* fp32 [C][C][3]                        */
+  const float* bias;        /* fp32 [C]                              */
+  const void* residual;     /* bf16 [B][T][C] or NULL                */
+  const float* scale_shift; /* fp32 [B][ss_stride] or NULL: apply LN+FiLM */
+  double* stats_out;        /* fp64 [B][groups][2] or NULL           */
+  int32_t ss_stride;
+  int32_t B, T, C, groups;
+  float gn_eps, ln_eps;
+} adp_narrow_conv_args;
+int adp_narrow_conv(const adp_narrow_conv_args* args, adp_stream_t stream);
+
+/* y = bf16(SiLU(x)) elementwise: the SiLU in front of every Modulation.to_scale_shift /
+ * MergeModulate.to_scale linear (a_unet), applied once to the shared feature vector. */
+int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t stream);
+
+/* VSampler step on its own (reference diffusion.py:185-187), for nets that do not end in
+ * adp_stem_out:  x_next = a1*(a0*x - b0*v) + b1*(b0*x + a0*v),  ab = [a0,b0,a1,b1]. */
+int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_next, int64_t n,
+                     adp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADP_B200_H_ */

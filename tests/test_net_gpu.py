@@ -1,0 +1,178 @@
+"""Whole-path parity on the GPU: the B200 UNetV0 / VSampler / model wrappers against
+ (a) the committed golden vectors (made by oracle/make_golden.py from the UNMODIFIED
+     reference files running on the a_unet shim), and
+ (b) the CPU oracle port evaluated here on the same seeded inputs,
+plus size-independent properties at the README (BASELINE) configuration.
+
+Stated bf16 tolerance (north_star: "stated bf16 tolerance"): storage is bf16 with fp32
+accumulation, so every activation carries ~2^-9 relative rounding.  The net output is
+v = x + gate*branch with |branch| << |x| at initialisation, so two metrics are bounded:
+  * rel-L2 error of v                      <= 1e-3   (the fp32 rtol of the north star)
+  * rel-L2 error of the branch (v - skip)  <= BRANCH_TOL = 3e-2
+    (the fp32 oracle evaluated under bf16 autocast on CPU differs from itself by 5.8e-3 on
+     the same metric -- stored in the golden file as bf16_err_branch)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BRANCH_TOL = 3e-2
+V_TOL = 1e-3
+
+TINY = dict(in_channels=2, channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2],
+            attentions=[0, 0, 1], attention_heads=2, attention_features=64)
+TINY_TEXT = dict(TINY, cross_attentions=[0, 1, 1], use_embedding_cfg=True,
+                 embedding_max_length=8, embedding_features=32)
+TINY_NOATT = dict(channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def fingerprint(module):
+    ps = [p.detach().double() for p in module.parameters()]
+    return np.array([sum(float(p.sum()) for p in ps), sum(float(p.abs().sum()) for p in ps),
+                     float(sum(p.numel() for p in ps))])
+
+
+@pytest.fixture(scope="module")
+def adp():
+    import audio_diffusion_pytorch_b200 as adp
+    return adp
+
+
+def load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a)).to(DEV)
+
+
+def check(v, v_ref, skip, what, branch_tol=BRANCH_TOL):
+    e_v, e_b = rel_l2(v, v_ref), rel_l2(v.cpu() - skip.cpu(), v_ref.cpu() - skip.cpu())
+    print(f"{what}: rel-L2(v) {e_v:.3e}  rel-L2(branch) {e_b:.3e}")
+    assert e_v <= V_TOL, f"{what}: v error {e_v:.3e} > {V_TOL}"
+    assert e_b <= branch_tol, f"{what}: branch error {e_b:.3e} > {branch_tol}"
+
+
+def test_unconditional_net_and_sampler_vs_golden(adp, oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_unconditional.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**TINY)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    x, sigma = t(g["x"]), t(g["sigma"])
+    v_ref = torch.from_numpy(g["v"])
+    print("oracle-under-bf16 errors stored in golden:", float(g["bf16_err_net"]),
+          float(g["bf16_err_branch"]), float(g["bf16_err_sample5"]))
+    for call in range(3):       # eager, graph capture, graph replay must agree
+        v = model.net(x, sigma)
+        check(v, v_ref, x, f"UNetV0 forward (call {call})")
+    noise = t(g["noise"])
+    s = model.sample(noise, num_steps=5)
+    e = rel_l2(s, torch.from_numpy(g["sample5"]))
+    print(f"VSampler 5 steps: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    assert torch.equal(noise, t(g["noise"])), "sample() must not mutate its input"
+
+
+def test_text_cfg_vs_golden(adp, oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_text_cfg.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**TINY_TEXT)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY_TEXT).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    x, sigma, emb = t(g["x"]), t(g["sigma"]), t(g["embedding"])
+    v1 = model.net(x, sigma, embedding=emb)
+    check(v1, torch.from_numpy(g["v_scale1"]), x, "text-cond forward, scale 1")
+    v5 = model.net(x, sigma, embedding=emb, embedding_scale=5.0)
+    # guidance extrapolates: v_m + 5 (v_c - v_m) amplifies the branch error by up to ~9x
+    check(v5, torch.from_numpy(g["v_scale5"]), x, "text-cond forward, CFG 5", branch_tol=0.15)
+    s = model.sample(t(g["noise"]), num_steps=3, embedding=emb, embedding_scale=5.0)
+    e = rel_l2(s, torch.from_numpy(g["sample3"]))
+    print(f"CFG sampler 3 steps: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+
+
+def test_upsampler_and_vocoder_sample_vs_golden(adp, oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_upsampler.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **TINY_NOATT)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2,
+                                   **TINY_NOATT).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    s = model.sample(t(g["low"]), num_steps=3, generator=torch.Generator().manual_seed(5))
+    e = rel_l2(s, torch.from_numpy(g["sample3"]))
+    print(f"DiffusionUpsampler.sample: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    e = rel_l2(model.reupsample(t(g["audio"])), torch.from_numpy(g["reupsampled"]))
+    assert e <= 1e-5, f"reupsample {e}"
+
+    g = load(golden_dir, "tiny_vocoder.npz")
+    kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True,
+              **TINY_NOATT)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionVocoderPort(**kw)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionVocoder(net_t=adp.UNetV0, **kw).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.to_flat.load_state_dict(ref.to_flat.state_dict())
+    s = model.sample(t(g["mel"]), num_steps=3, generator=torch.Generator().manual_seed(8))
+    e = rel_l2(s, torch.from_numpy(g["sample3"]))
+    print(f"DiffusionVocoder.sample: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+
+
+def test_sampler_algebra_generic_net(adp, golden_dir):
+    """VSampler around an arbitrary net (not the B200 U-Net): pins the fused step kernel."""
+    g = load(golden_dir, "sampler_toy.npz")
+
+    class Toy(torch.nn.Module):
+        def forward(self, x, tt, **kw):
+            return 0.5 * x * tt.view(-1, 1, 1) + torch.sin(x)
+
+    out = adp.VSampler(net=Toy())(t(g["x"]), num_steps=7)
+    np.testing.assert_allclose(out.cpu().numpy(), g["out7"], rtol=1e-4, atol=1e-5)
+
+
+README = dict(in_channels=2, channels=[8, 32, 64, 128, 256, 512, 512, 1024, 1024],
+              factors=[1, 4, 4, 4, 2, 2, 2, 2, 2], items=[1, 2, 2, 2, 2, 2, 2, 4, 4],
+              attentions=[0, 0, 0, 0, 0, 1, 1, 1, 1], attention_heads=8, attention_features=64)
+
+
+def test_readme_config_properties_full_size(adp, oracle_port):
+    """BASELINE config at full size ([B,2,2^18]): properties that need no oracle run --
+    batch independence, call-to-call reproducibility, finite output -- plus a level-by-level
+    oracle comparison on a shorter clip of the SAME network (2^13 samples keeps the CPU
+    oracle in seconds; every kernel shape class of the 9-level net is exercised)."""
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**README)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **README).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    g = torch.Generator().manual_seed(11)
+    x_small = torch.randn(2, 2, 2 ** 13, generator=g)
+    sig = torch.rand(2, generator=g)
+    with torch.no_grad():
+        v_ref = ref.net(x_small, sig)
+    v = model.net(x_small.to(DEV), sig.to(DEV))
+    check(v, v_ref, x_small, "README net, T=2^13 vs CPU oracle")
+
+    x = torch.randn(2, 2, 2 ** 18, generator=g).to(DEV)
+    sig2 = torch.tensor([0.3, 0.8], device=DEV)
+    v2 = model.net(x, sig2)
+    assert torch.isfinite(v2).all()
+    v2b = model.net(x, sig2)
+    assert rel_l2(v2b - x, v2 - x) < 1e-3, "call-to-call reproducibility"
+    v1 = model.net(x[:1], sig2[:1])
+    e = rel_l2(v1 - x[:1], v2[:1] - x[:1])
+    print(f"batch independence (branch rel-L2): {e:.3e}")
+    assert e < 2e-2
