@@ -2,9 +2,13 @@
 CUDA stream) and the host-side weight packers for adp_conv_gemm.
 
 Activations are channels-last bf16 [B, T, C]; statistics fp64 [B, G, 2]; conditioning fp32.
+
+`with ops.trace(timing=True) as tr:` records, for every launch made inside it, a label, the
+algorithmic FLOPs / bytes of that launch and (optionally) CUDA events around it -- bench.py's
+roofline and `gpu_launches` come from this, not from a side table.
 """
 import ctypes as C
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 from torch import Tensor
@@ -25,6 +29,63 @@ def _stream():
 
 def device_check() -> None:
     _lib.check(_lib.lib().adp_device_check(), "adp_device_check")
+
+
+# -------------------------------------------------------------------------------- tracing
+_TRACE = None
+
+
+class trace:
+    """Context manager collecting one record per kernel launch."""
+
+    def __init__(self, timing: bool = False):
+        self.timing, self.records = timing, []  # type: bool, List[dict]
+
+    def __enter__(self):
+        global _TRACE
+        self._prev, _TRACE = _TRACE, self
+        return self
+
+    def __exit__(self, *exc):
+        global _TRACE
+        _TRACE = self._prev
+
+    def table(self):
+        """Aggregated by label: count, avg / total ms (after a sync), flops & bytes per launch."""
+        if self.timing:
+            torch.cuda.synchronize()
+        out = {}
+        for r in self.records:
+            row = out.setdefault(r["name"], {"name": r["name"], "count": 0, "ms_total": 0.0,
+                                             "flops": r["flops"], "bytes": r["bytes"]})
+            row["count"] += 1
+            if self.timing:
+                row["ms_total"] += r["e0"].elapsed_time(r["e1"])
+        for row in out.values():
+            row["ms_avg"] = row["ms_total"] / row["count"]
+        return out
+
+
+def _launch(fn, what: str, meta):
+    """meta: callable -> (label, flops, bytes); evaluated only while tracing."""
+    tr = _TRACE
+    if tr is None:
+        _lib.check(fn(), what)
+        return
+    label, flops, nbytes = meta()
+    rec = {"name": label, "flops": float(flops), "bytes": float(nbytes)}
+    if tr.timing:
+        rec["e0"] = torch.cuda.Event(enable_timing=True)
+        rec["e1"] = torch.cuda.Event(enable_timing=True)
+        rec["e0"].record()
+    _lib.check(fn(), what)
+    if tr.timing:
+        rec["e1"].record()
+    tr.records.append(rec)
+
+
+def _nb(*tensors) -> int:
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
 # ------------------------------------------------------------------------------ packers
@@ -90,32 +151,44 @@ def conv_gemm(a: Tensor, w: Tensor, out: Tensor, *, c_in: int, n_valid: int,
     args.up_factor, args.groups, args.block_n = up_factor, groups, block_n
     args.out_fp32 = 1 if out.dtype == torch.float32 else 0
     args.ld_gate = 0 if gate is None else gate.stride(0)
-    _lib.check(_lib.lib().adp_conv_gemm(C.byref(args), _stream()), "adp_conv_gemm")
+
+    def meta():
+        rows = B * T
+        tap_sum = len(taps) if up_factor <= 1 else (4 if up_factor == 2 else up_factor + 2)
+        kind = "up%d" % up_factor if up_factor > 1 else "k%d" % len(taps)
+        flops = 2.0 * rows * c_in * n_valid * tap_sum
+        nbytes = rows * c_in * 2 + w.shape[0] * min(w.shape[1], tap_sum * c_in) * 2 \
+            + rows * phases * n_valid * out.element_size() * (2 if residual is not None else 1)
+        return f"conv_gemm[{kind} M={rows} K={c_in} N={n_valid}x{phases}]", flops, nbytes
+
+    _launch(lambda: _lib.lib().adp_conv_gemm(C.byref(args), _stream()), "adp_conv_gemm", meta)
     return out
 
 
 def gn_silu(x: Tensor, y: Tensor, stats: Tensor, gamma: Tensor, beta: Tensor, groups: int,
             eps: float = 1e-5) -> Tensor:
     B, T, Cc = x.shape
-    _lib.check(_lib.lib().adp_gn_silu(x.data_ptr(), y.data_ptr(), stats.data_ptr(),
-                                      gamma.data_ptr(), beta.data_ptr(), B, T, Cc, groups, eps,
-                                      _stream()), "adp_gn_silu")
+    _launch(lambda: _lib.lib().adp_gn_silu(x.data_ptr(), y.data_ptr(), stats.data_ptr(),
+                                           gamma.data_ptr(), beta.data_ptr(), B, T, Cc, groups,
+                                           eps, _stream()), "adp_gn_silu",
+            lambda: (f"gn_silu[M={B * T} C={Cc}]", 0, _nb(x, y)))
     return y
 
 
 def gn_stats(x: Tensor, stats: Tensor, groups: int) -> Tensor:
     B, T, Cc = x.shape
-    _lib.check(_lib.lib().adp_gn_stats(x.data_ptr(), stats.data_ptr(), B, T, Cc, groups,
-                                       _stream()), "adp_gn_stats")
+    _launch(lambda: _lib.lib().adp_gn_stats(x.data_ptr(), stats.data_ptr(), B, T, Cc, groups,
+                                            _stream()), "adp_gn_stats",
+            lambda: (f"gn_stats[M={B * T} C={Cc}]", 0, _nb(x)))
     return stats
 
 
 def ln_film(x: Tensor, y: Tensor, scale_shift: Optional[Tensor] = None, ss_stride: int = 0,
             stats_out: Optional[Tensor] = None, groups: int = 8, eps: float = 1e-6) -> Tensor:
     B, T, Cc = x.shape
-    _lib.check(_lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
-                                      _p(stats_out), B, T, Cc, groups, eps, _stream()),
-               "adp_ln_film")
+    _launch(lambda: _lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
+                                           _p(stats_out), B, T, Cc, groups, eps, _stream()),
+            "adp_ln_film", lambda: (f"ln_film[M={B * T} C={Cc}]", 0, _nb(x, y)))
     return y
 
 
@@ -123,26 +196,37 @@ def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: flo
     """q: bf16 view [B, Tq, >=heads*64] (row pitch = stride(1)); k, v over Tk rows."""
     B, Tq = q.shape[0], q.shape[1]
     Tk = k.shape[1]
-    _lib.check(_lib.lib().adp_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B,
-                                        heads, Tq, Tk, q.stride(1), k.stride(1), v.stride(1),
-                                        o.stride(1), scale, _stream()), "adp_attention")
+    _launch(lambda: _lib.lib().adp_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
+                                             B, heads, Tq, Tk, q.stride(1), k.stride(1),
+                                             v.stride(1), o.stride(1), scale, _stream()),
+            "adp_attention",
+            lambda: (f"attention[B={B} H={heads} Tq={Tq} Tk={Tk}]", 4.0 * B * heads * Tq * Tk * 64,
+                     (2 * B * Tq + 2 * B * Tk) * heads * 64 * 2))
     return o
 
 
 def skinny_linear(x: Tensor, w: Tensor, bias: Optional[Tensor], y: Tensor, K: int, N: int,
                   in_act: int = ACT_NONE, out_act: int = ACT_NONE) -> Tensor:
-    _lib.check(_lib.lib().adp_skinny_linear(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(),
-                                            x.shape[0], K, N, x.stride(0), w.stride(0),
-                                            y.stride(0), in_act, out_act, _stream()),
-               "adp_skinny_linear")
+    _launch(lambda: _lib.lib().adp_skinny_linear(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(),
+                                                 x.shape[0], K, N, x.stride(0), w.stride(0),
+                                                 y.stride(0), in_act, out_act, _stream()),
+            "adp_skinny_linear",
+            lambda: (f"skinny_linear[B={x.shape[0]} K={K} N={N}]", 2.0 * x.shape[0] * K * N, _nb(w)))
     return y
 
 
 def time_features(sigma: Tensor, freqs: Tensor, out: Tensor) -> Tensor:
-    _lib.check(_lib.lib().adp_time_features(sigma.data_ptr(), freqs.data_ptr(), out.data_ptr(),
-                                            sigma.shape[0], freqs.shape[0], out.stride(0),
-                                            _stream()), "adp_time_features")
+    _launch(lambda: _lib.lib().adp_time_features(sigma.data_ptr(), freqs.data_ptr(), out.data_ptr(),
+                                                 sigma.shape[0], freqs.shape[0], out.stride(0),
+                                                 _stream()), "adp_time_features",
+            lambda: ("time_features", 0, _nb(out)))
     return out
+
+
+def silu_bf16(x: Tensor, y: Tensor) -> Tensor:
+    _launch(lambda: _lib.lib().adp_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()),
+            "adp_silu_bf16", lambda: ("silu_bf16", 0, _nb(x, y)))
+    return y
 
 
 def stem_in(x: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, f: int, *,
@@ -155,7 +239,9 @@ def stem_in(x: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, f: int, *
     a.B, a.cx, a.T = x.shape
     a.ca = 0 if append is None else append.shape[1]
     a.c0, a.f, a.groups = w.shape[0], f, groups
-    _lib.check(_lib.lib().adp_stem_in(C.byref(a), _stream()), "adp_stem_in")
+    _launch(lambda: _lib.lib().adp_stem_in(C.byref(a), _stream()), "adp_stem_in",
+            lambda: (f"stem_in[B={x.shape[0]} T={x.shape[2]} c0={w.shape[0]}]",
+                     2.0 * out.numel() * w.shape[1] * w.shape[2], _nb(x, append, noise, out)))
     return out
 
 
@@ -177,7 +263,10 @@ def stem_out(h: Tensor, x: Tensor, w: Tensor, bias: Optional[Tensor], gate: Tens
     a.ca = 0 if append is None else append.shape[1]
     a.c0, a.co, a.f = h.shape[-1], w.shape[0], f
     a.ld_gate = gate.stride(0)
-    _lib.check(_lib.lib().adp_stem_out(C.byref(a), _stream()), "adp_stem_out")
+    _launch(lambda: _lib.lib().adp_stem_out(C.byref(a), _stream()), "adp_stem_out",
+            lambda: (f"stem_out[B={x.shape[0]} T={x.shape[2]} c0={h.shape[-1]}]",
+                     2.0 * h.shape[0] * x.shape[2] * w.numel(),
+                     _nb(h, x, append, noise, v_out, x_next, dv)))
 
 
 def narrow_conv(x: Tensor, y: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor, w: Tensor,
@@ -192,18 +281,15 @@ def narrow_conv(x: Tensor, y: Tensor, stats_in: Tensor, gamma: Tensor, beta: Ten
     a.ss_stride = ss_stride
     a.B, a.T, a.C = x.shape
     a.groups, a.gn_eps, a.ln_eps = groups, gn_eps, ln_eps
-    _lib.check(_lib.lib().adp_narrow_conv(C.byref(a), _stream()), "adp_narrow_conv")
-    return y
-
-
-def silu_bf16(x: Tensor, y: Tensor) -> Tensor:
-    _lib.check(_lib.lib().adp_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()),
-               "adp_silu_bf16")
+    _launch(lambda: _lib.lib().adp_narrow_conv(C.byref(a), _stream()), "adp_narrow_conv",
+            lambda: (f"narrow_conv[M={x.shape[0] * x.shape[1]} C={x.shape[2]}"
+                     f"{' +res+film' if residual is not None else ''}]",
+                     2.0 * x.numel() * 3 * x.shape[2], _nb(x, y, residual)))
     return y
 
 
 def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:
-    _lib.check(_lib.lib().adp_sampler_step(x.data_ptr(), v.data_ptr(), ab.data_ptr(),
-                                           x_next.data_ptr(), x.numel(), _stream()),
-               "adp_sampler_step")
+    _launch(lambda: _lib.lib().adp_sampler_step(x.data_ptr(), v.data_ptr(), ab.data_ptr(),
+                                                x_next.data_ptr(), x.numel(), _stream()),
+            "adp_sampler_step", lambda: ("sampler_step", 0, _nb(x, v, x_next)))
     return x_next

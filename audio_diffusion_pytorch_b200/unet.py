@@ -136,6 +136,7 @@ class _Plan:
         self.prog: List[Callable[[], None]] = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.n_launches = 0
+        self.n_kernels = 0
         self.runs = 0
 
     def add(self, fn: Callable[[], None]) -> None:
@@ -570,6 +571,18 @@ class B200UNet(nn.Module):
             plan = self._plans[key] = self._build_plan(B, T, Bh, M, mode)
         return plan
 
+    def profile_plan(self, plan: _Plan, iters: int = 5):
+        """Instrumented eager passes of a plan: CUDA events around every launch, aggregated
+        per kernel/shape -> {label: count per pass, avg/total ms per pass, flops, bytes}."""
+        with ops.trace(timing=True) as tr:
+            for _ in range(iters):
+                plan.run_eager()
+        table = tr.table()
+        for row in table.values():
+            row["count"] //= iters
+            row["ms_total"] /= iters
+        return table
+
     def _execute(self, plan: _Plan) -> None:
         """First call eager (validates every launch), second call captures, then replays."""
         if not self.use_cuda_graph:
@@ -577,7 +590,9 @@ class B200UNet(nn.Module):
         elif plan.graph is not None:
             plan.graph.replay()
         elif plan.runs == 0:
-            plan.run_eager()
+            with ops.trace() as tr:          # also counts the kernels of one net evaluation
+                plan.run_eager()
+            plan.n_kernels = len(tr.records)
         else:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
