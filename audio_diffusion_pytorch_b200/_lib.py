@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
     L.adp_version.restype = i32
     sig = {
         "adp_device_check": [],
+        "adp_debug_set": [i32, i32],
         "adp_conv_gemm": [C.POINTER(ConvGemmArgs), vp],
         "adp_gn_silu": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "adp_gn_stats": [vp, vp, i32, i32, i32, i32, vp],
@@ -88,4 +89,4 @@ def check(rc: int, what: str) -> None:
 EXPORTS = ["adp_version", "adp_last_error", "adp_device_check", "adp_conv_gemm", "adp_gn_silu",
            "adp_gn_stats", "adp_ln_film", "adp_attention", "adp_skinny_linear",
            "adp_time_features", "adp_stem_in", "adp_stem_out", "adp_narrow_conv",
-           "adp_sampler_step", "adp_silu_bf16"]
+           "adp_sampler_step", "adp_silu_bf16", "adp_debug_set"]

@@ -1,24 +1,35 @@
-// adp_conv_gemm: shifted-tap GEMM on tcgen05 (see include/adp_b200.h).
+// adp_conv_gemm: persistent shifted-tap GEMM on tcgen05 (see include/adp_b200.h).
 //
 // GEMM view (swapped w.r.t. the usual conv-as-GEMM so that one accumulator ROW is one time
 // position): D[m = time position, n = output channel] = sum_{tap,k} A[m + off(tap), k] * W[n, tap, k]
-//   A: channels-last activations  -> K-major operand, TMA box [BK x 128 rows], rows shifted
-//      per tap; rows outside [0,T) are zero-filled by TMA = the conv's zero padding.
-//   W: packed weights [N][taps*C_in] -> K-major operand, TMA box [BK x BN].
-//   D: fp32 in TMEM, 128 lanes (rows) x BN columns.
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA
-// producer + TMEM allocator, warp 5 MMA issuer.  smem ring of `stages` {A,W} tiles with
-// full/empty mbarriers; tcgen05.commit releases ring slots and publishes the accumulator.
+//   A: channels-last activations -> K-major operand.  ONE TMA box of (128 + span) rows per
+//      64-channel chunk serves all taps: tap j is the same smem tile read through a UMMA
+//      descriptor whose start address is advanced by j rows.  Rows outside [0,T) are
+//      zero-filled by TMA = the conv's zero padding.
+//   W: packed weights [N][taps*C_in] -> K-major operand, own smem ring (one box per tap+chunk).
+//   D: fp32 in TMEM, 128 lanes x BN columns, DOUBLE buffered: the epilogue of tile i drains
+//      buffer i&1 while the MMAs of tile i+1 fill the other one.
+// Persistent: grid = #SMs, CTA c walks tiles c, c+grid, ... (n fastest: the CTAs of one wave
+// share A tiles through L2).  Warp roles (192 threads): warp 0 TMA producer + TMEM allocator,
+// warp 1 MMA issuer, warps 2-5 epilogue (TMEM lane quarter = warp & 3).  The epilogue
+// prefetches the residual rows of its tile into registers while the tile's MMAs still run.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace adp {
 
+int conv_gemm_v1(const adp_conv_gemm_args* args, adp_stream_t stream);
+
+// debug / A-B switches (adp_debug_set): [0] impl 2=persistent 1=v1; [1] single A load for all
+// taps; [2] descriptor base_offset mode for row-shifted starts (0: zero, 1: (addr>>7)&7)
+int g_debug[8] = {2, 1, 0, 0, 0, 0, 0, 0};
+
 constexpr int kBM = 128;
-constexpr int kMaxStages = 6;
+constexpr int kMaxNA = 4;
+constexpr int kMaxNW = 8;
 constexpr int kMaxGroups = 32;
 
-struct GemmParams {
+struct Gemm2Params {
   __nv_bfloat16* out;
   const __nv_bfloat16* residual;
   const float* bias;
@@ -28,66 +39,77 @@ struct GemmParams {
   int n_pad, n_valid;
   int ntaps, tap_off0, tap_off1, tap_off2, up_factor;
   int groups, group_size;
-  int stages;
-  int out_fp32;
-  int ld_gate;
+  int out_fp32, ld_gate;
+  int n_tiles_n, total_tiles;
+  int a_rows;        // rows per A box (128 + tap span) when single_load, else 128
+  int single_load;
+  int na, nw;        // ring depths
+  int a_stage_bytes, w_stage_bytes;
+  int base_off_mode;
 };
 
-template <int BN, int SW>
-struct GemmCfg {
-  static constexpr int BK = SW / 2;             // bf16 elements per swizzle row
-  static constexpr int A_BYTES = kBM * SW;
-  static constexpr int W_TX_BYTES = BN * SW;    // bytes TMA actually writes
-  static constexpr int W_BYTES = (W_TX_BYTES + 1023) / 1024 * 1024;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int CH = BN < 32 ? 16 : 32;  // epilogue column chunk
+template <int SW>
+__device__ __forceinline__ uint64_t desc_kmajor_shifted(uint32_t addr, int base_off_mode) {
+  uint64_t d = umma_desc_kmajor<SW>(addr);
+  if (base_off_mode) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
+  return d;
+}
+
+struct TileInfo {
+  int b, t0, n0, phase, ch0, ntaps, min_off, row0, row1, row2;
 };
 
+__device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, int BN) {
+  TileInfo ti;
+  const int m_tile = tile / p.n_tiles_n;
+  const int n_tile = tile - m_tile * p.n_tiles_n;
+  ti.b = m_tile / p.tiles_per_batch;
+  ti.t0 = (m_tile - ti.b * p.tiles_per_batch) * kBM;
+  ti.n0 = n_tile * BN;
+  ti.phase = ti.n0 / p.n_pad;
+  ti.ch0 = ti.n0 - ti.phase * p.n_pad;
+  if (p.up_factor > 1) {   // nearest-upsample + conv3: taps collapse per output phase
+    if (ti.phase == 0) { ti.ntaps = 2; ti.min_off = -1; }
+    else if (ti.phase == p.up_factor - 1) { ti.ntaps = 2; ti.min_off = 0; }
+    else { ti.ntaps = 1; ti.min_off = 0; }
+    ti.row0 = 0; ti.row1 = 1; ti.row2 = 2;
+  } else {
+    ti.ntaps = p.ntaps;
+    ti.min_off = p.tap_off0;
+    ti.row0 = 0; ti.row1 = p.tap_off1 - p.tap_off0; ti.row2 = p.tap_off2 - p.tap_off0;
+  }
+  return ti;
+}
+
 template <int BN, int SW>
-__global__ void __launch_bounds__(192)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const GemmParams p) {
-  using Cfg = GemmCfg<BN, SW>;
+__global__ void __launch_bounds__(192, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const Gemm2Params p) {
+  constexpr int BK = SW / 2;
+  constexpr int ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns per accumulator buffer
+  constexpr int CH = BN < 32 ? 16 : 32;           // epilogue column chunk
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kMaxStages];
-  __shared__ uint64_t empty_bar[kMaxStages];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t a_full[kMaxNA], a_empty[kMaxNA];
+  __shared__ uint64_t w_full[kMaxNW], w_empty[kMaxNW];
+  __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_stats[2 * kMaxGroups];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-
-  const int m_tile = blockIdx.x;
-  const int b = m_tile / p.tiles_per_batch;
-  const int t0 = (m_tile - b * p.tiles_per_batch) * kBM;
-  const int n0 = blockIdx.y * BN;          // in the padded [phases*n_pad] space
-  const int phase = n0 / p.n_pad;
-  const int ch0 = n0 - phase * p.n_pad;    // channel offset inside the phase
-
-  int ntaps = p.ntaps, off0 = p.tap_off0, off1 = p.tap_off1, off2 = p.tap_off2;
-  if (p.up_factor > 1) {  // nearest-upsample + conv3: taps collapse per output phase
-    if (phase == 0) { ntaps = 2; off0 = -1; off1 = 0; }
-    else if (phase == p.up_factor - 1) { ntaps = 2; off0 = 0; off1 = 1; }
-    else { ntaps = 1; off0 = 0; }
-  }
-  const int k_chunks = p.c_in / Cfg::BK;
-  const int iters = ntaps * k_chunks;
-  const int stages = p.stages;
+  uint8_t* a_ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* w_ring = a_ring + p.na * p.a_stage_bytes;
+  const int k_chunks = p.c_in / BK;
 
   if (threadIdx.x < 2 * kMaxGroups) s_stats[threadIdx.x] = 0.f;
-  if (warp == 4) {
-    tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 2 * ACC_COLS);
     tmem_relinquish();
-  } else if (warp == 5 && lane == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&tmem_full_bar, 1);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.nw; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -97,125 +119,206 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ---------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = it / k_chunks;
-        const int kc = it - tap * k_chunks;
-        const int off = tap == 0 ? off0 : (tap == 1 ? off1 : off2);
-        uint8_t* a_s = tiles + s * Cfg::STAGE_BYTES;
-        uint8_t* w_s = a_s + Cfg::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::A_BYTES + Cfg::W_TX_BYTES);
-        tma_load_3d(a_s, &tmA, &full_bar[s], kc * Cfg::BK, t0 + off, b);
-        tma_load_2d(w_s, &tmW, &full_bar[s], tap * p.c_in + kc * Cfg::BK, n0);
+      uint32_t ia = 0, iw = 0;
+      const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * SW;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo ti = tile_info(p, tile, BN);
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          if (p.single_load) {
+            const uint32_t sa = ia % p.na;
+            mbar_wait(&a_empty[sa], ((ia / p.na) & 1) ^ 1);
+            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+            tma_load_3d(a_ring + sa * p.a_stage_bytes, &tmA, &a_full[sa], kc * BK,
+                        ti.t0 + ti.min_off, ti.b);
+            ++ia;
+          }
+          for (int tap = 0; tap < ti.ntaps; ++tap) {
+            if (!p.single_load) {
+              const int row = tap == 0 ? ti.row0 : (tap == 1 ? ti.row1 : ti.row2);
+              const uint32_t sa = ia % p.na;
+              mbar_wait(&a_empty[sa], ((ia / p.na) & 1) ^ 1);
+              mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+              tma_load_3d(a_ring + sa * p.a_stage_bytes, &tmA, &a_full[sa], kc * BK,
+                          ti.t0 + ti.min_off + row, ti.b);
+              ++ia;
+            }
+            const uint32_t sw = iw % p.nw;
+            mbar_wait(&w_empty[sw], ((iw / p.nw) & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[sw], BN * SW);
+            tma_load_2d(w_ring + sw * p.w_stage_bytes, &tmW, &w_full[sw], tap * p.c_in + kc * BK,
+                        ti.n0);
+            ++iw;
+          }
+        }
       }
     }
-  } else if (warp == 5) {
-    // -------------------------------------------------------------------- MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t ia = 0, iw = 0, j = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+        const TileInfo ti = tile_info(p, tile, BN);
+        const uint32_t buf = j & 1;
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
-        const uint32_t w_addr = a_addr + Cfg::A_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < k_chunks; ++kc) {
+          uint32_t sa = ia % p.na;
+          if (p.single_load) mbar_wait(&a_full[sa], (ia / p.na) & 1);
+          for (int tap = 0; tap < ti.ntaps; ++tap) {
+            int row = 0;
+            if (p.single_load) {
+              row = tap == 0 ? ti.row0 : (tap == 1 ? ti.row1 : ti.row2);
+            } else {
+              sa = ia % p.na;
+              mbar_wait(&a_full[sa], (ia / p.na) & 1);
+            }
+            const uint32_t sw = iw % p.nw;
+            mbar_wait(&w_full[sw], (iw / p.nw) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_ring + sa * p.a_stage_bytes) + row * SW;
+            const uint32_t w_addr = smem_u32(w_ring + sw * p.w_stage_bytes);
 #pragma unroll
-        for (int kk = 0; kk < Cfg::BK / 16; ++kk) {
-          umma_bf16(tmem_base, umma_desc_kmajor<SW>(a_addr + kk * 32),
-                    umma_desc_kmajor<SW>(w_addr + kk * 32), idesc, (it | kk) != 0);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              umma_bf16(d_tmem, desc_kmajor_shifted<SW>(a_addr + kk * 32, p.base_off_mode),
+                        umma_desc_kmajor<SW>(w_addr + kk * 32), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&w_empty[sw]);
+            ++iw;
+            if (!p.single_load) { umma_commit(&a_empty[sa]); ++ia; }
+          }
+          if (p.single_load) { umma_commit(&a_empty[sa]); ++ia; }
         }
-        umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ---------------------------------------------------------------------- epilogue
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = t < p.T;
-    const size_t row_off = (static_cast<size_t>(b) * p.T + (row_ok ? t : 0)) * p.ldo +
-                           static_cast<size_t>(phase) * p.n_valid;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // -------------------------------------------------------------------------- epilogue
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const bool do_stats = p.stats != nullptr;
+    const int et = threadIdx.x - 64;        // 0..127 among epilogue threads
     GroupStatAcc acc;
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += Cfg::CH) {
-      uint32_t r[Cfg::CH];
-      if constexpr (Cfg::CH == 16) tmem_ld16(taddr + c0, r);
-      else tmem_ld32(taddr + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int v8 = 0; v8 < Cfg::CH / 8; ++v8) {
-        const int ch = ch0 + c0 + v8 * 8;       // first channel of this 8-vector
-        if (ch >= p.n_valid) continue;           // padded columns (uniform branch)
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[v8 * 8 + j]);
-        if (p.bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.gate) {
-          const float* gp = p.gate + static_cast<size_t>(b) * p.ld_gate + ch;
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
-          v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-          v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-        }
-        if (p.out_fp32) {
-          if (row_ok) {
-            float* op = reinterpret_cast<float*>(p.out) + row_off + ch;
-            *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    int cur_b = -1;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      const TileInfo ti = tile_info(p, tile, BN);
+      const uint32_t buf = j & 1;
+      const int t = ti.t0 + row;
+      const bool row_ok = t < p.T;
+      const size_t row_off = (static_cast<size_t>(ti.b) * p.T + (row_ok ? t : 0)) * p.ldo +
+                             static_cast<size_t>(ti.phase) * p.n_valid;
+      if (do_stats && ti.b != cur_b) {
+        if (cur_b >= 0) {   // publish the finished batch's partial sums
+          acc.flush(s_stats, lane);
+          acc.cur_g = -1;
+          named_bar_sync(1, 128);
+          if (et < 2 * p.groups) {
+            const float val = s_stats[et];
+            if (val != 0.f)
+              atomicAdd(p.stats + static_cast<size_t>(cur_b) * 2 * p.groups + et,
+                        static_cast<double>(val));
+            s_stats[et] = 0.f;
           }
-          continue;
+          named_bar_sync(1, 128);
         }
-        if (row_ok) {
-          if (p.residual) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + row_off + ch);
-            const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y);
-            const float2 r2 = unpack_bf16(rr.z), r3 = unpack_bf16(rr.w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-          }
-          uint4 o;
-          o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-          o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(p.out + row_off + ch) = o;
-          if (do_stats) {  // statistics of the ROUNDED values the next layer will read
-            const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y);
-            const float2 q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
-            v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
-          }
-        } else {
+        cur_b = ti.b;
+      }
+      // residual rows of this tile -> registers, while the tile's MMAs are still running
+      uint4 res[BN / 8];
+      if (p.residual) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        }
-        if (do_stats) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc.add(v[j], (ch + j) / p.group_size, s_stats, lane);
+        for (int i = 0; i < BN / 8; ++i) {
+          const int ch = ti.ch0 + i * 8;
+          res[i] = make_uint4(0, 0, 0, 0);
+          if (row_ok && ch < p.n_valid)
+            res[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + row_off + ch));
         }
       }
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * ACC_COLS + lane_addr;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t r[CH];
+        if constexpr (CH == 16) tmem_ld16(taddr + c0, r);
+        else tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v8 = 0; v8 < CH / 8; ++v8) {
+          const int ch = ti.ch0 + c0 + v8 * 8;
+          if (ch >= p.n_valid) continue;           // padded columns (uniform)
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[v8 * 8 + i]);
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.gate) {
+            const float* gp = p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+            v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+            v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+          }
+          if (p.out_fp32) {
+            if (row_ok) {
+              float* op = reinterpret_cast<float*>(p.out) + row_off + ch;
+              *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            continue;
+          }
+          if (row_ok) {
+            if (p.residual) {
+              const uint4 rr = res[(c0 + v8 * 8) / 8];
+              const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y);
+              const float2 r2 = unpack_bf16(rr.z), r3 = unpack_bf16(rr.w);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(p.out + row_off + ch) = o;
+            if (do_stats) {  // statistics of the ROUNDED values the next layer will read
+              const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y);
+              const float2 q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+              v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
+              v[4] = q2.x; v[5] = q2.y; v[6] = q3.x; v[7] = q3.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+          }
+          if (do_stats) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc.add(v[i], (ch + i) / p.group_size, s_stats, lane);
+          }
+        }
+      }
+      // accumulator buffer drained -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (do_stats) {
+    if (do_stats && cur_b >= 0) {
       acc.flush(s_stats, lane);
       named_bar_sync(1, 128);
-      if (threadIdx.x < 2 * p.groups) {
-        const float val = s_stats[threadIdx.x];
+      if (et < 2 * p.groups) {
+        const float val = s_stats[et];
         if (val != 0.f)
-          atomicAdd(p.stats + static_cast<size_t>(b) * 2 * p.groups + threadIdx.x,
+          atomicAdd(p.stats + static_cast<size_t>(cur_b) * 2 * p.groups + et,
                     static_cast<double>(val));
       }
     }
@@ -223,48 +326,70 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int SW>
-static int launch_gemm(const adp_conv_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, SW>;
+static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
+  constexpr int BK = SW / 2;
   const int tiles_per_batch = (a.T + kBM - 1) / kBM;
-  const int max_taps = a.up_factor > 1 ? 2 : a.ntaps;
-  const int iters_max = max_taps * (a.c_in / Cfg::BK);
+  const bool up = a.up_factor > 1;
+  const int max_taps = up ? 2 : a.ntaps;
+  const int span = up ? 1 : (a.ntaps > 1 ? a.tap_off[a.ntaps - 1] - a.tap_off[0] : 0);
+  const int single = (g_debug[1] != 0 && max_taps > 1) ? 1 : 0;
+  const int a_rows = single ? kBM + span : kBM;
+  const int k_chunks = a.c_in / BK;
+
+  Gemm2Params p;
+  p.a_stage_bytes = (a_rows * SW + 1023) / 1024 * 1024;
+  p.w_stage_bytes = (BN * SW + 1023) / 1024 * 1024;
+  // ring depths under ~196 KB: A boxes are reused by all taps, W boxes stream
+  const int a_iters = k_chunks * (single ? 1 : max_taps);
+  (void)a_iters;
+  int na = p.a_stage_bytes <= 9 * 1024 ? 4 : 3;   // the ring runs across tiles (persistent)
+  int nw = (196 * 1024 - na * p.a_stage_bytes) / p.w_stage_bytes;
+  if (nw > kMaxNW) nw = kMaxNW;
+  if (nw < 2) return set_error("adp_conv_gemm: tile does not fit shared memory");
+  p.na = na;
+  p.nw = nw;
+  const size_t smem = static_cast<size_t>(na) * p.a_stage_bytes +
+                      static_cast<size_t>(nw) * p.w_stage_bytes + 1024;
 
   CUtensorMap tmA, tmW;
   {
     const uint64_t dims[3] = {(uint64_t)a.c_in, (uint64_t)a.T, (uint64_t)a.B};
     const uint64_t strides[2] = {(uint64_t)a.lda * 2, (uint64_t)a.T * a.lda * 2};
-    const uint32_t box[3] = {(uint32_t)Cfg::BK, (uint32_t)kBM, 1};
+    const uint32_t box[3] = {(uint32_t)BK, (uint32_t)a_rows, 1};
     if (int e = make_tmap_bf16(&tmA, a.a, 3, dims, strides, box, SW)) return e;
   }
   {
     const uint64_t dims[2] = {(uint64_t)a.k_total, (uint64_t)a.phases * a.n_pad};
     const uint64_t strides[1] = {(uint64_t)a.k_total * 2};
-    const uint32_t box[2] = {(uint32_t)Cfg::BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
     if (int e = make_tmap_bf16(&tmW, a.w, 2, dims, strides, box, SW)) return e;
   }
 
-  int stages = iters_max < 4 ? iters_max : 4;
-  // keep several CTAs per SM resident on the short-K (bandwidth-bound) shapes
-  while (stages > 2 && stages * Cfg::STAGE_BYTES > 96 * 1024 && iters_max <= 6) --stages;
-  if (stages * Cfg::STAGE_BYTES > 200 * 1024) stages = (200 * 1024) / Cfg::STAGE_BYTES;
-  if (stages < 1) stages = 1;
-  const size_t smem = (size_t)stages * Cfg::STAGE_BYTES + 1024;
-
-  static size_t smem_attr = 0;   // opt-in dynamic smem (static smem counts against the 227 KB)
+  static size_t smem_attr = 0;
   if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, SW>,
+    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
 
-  GemmParams p;
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.residual = static_cast<const __nv_bfloat16*>(a.residual);
   p.bias = a.bias;
@@ -283,32 +408,43 @@ static int launch_gemm(const adp_conv_gemm_args& a, cudaStream_t stream) {
   p.up_factor = a.up_factor;
   p.groups = a.stats ? a.groups : 0;
   p.group_size = a.stats ? a.n_valid / a.groups : 1;
-  p.stages = stages;
   p.out_fp32 = a.out_fp32;
   p.ld_gate = a.ld_gate > 0 ? a.ld_gate : a.n_valid;
+  p.n_tiles_n = a.phases * a.n_pad / BN;
+  p.total_tiles = a.B * tiles_per_batch * p.n_tiles_n;
+  p.a_rows = a_rows;
+  p.single_load = single;
+  p.base_off_mode = g_debug[2];
 
-  dim3 grid(a.B * tiles_per_batch, a.phases * a.n_pad / BN);
-  conv_gemm_kernel<BN, SW><<<grid, 192, smem, stream>>>(tmA, tmW, p);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_gemm2_kernel<BN, SW><<<grid, 192, smem, stream>>>(tmA, tmW, p);
   ADP_LAUNCH_CHECK();
   return 0;
 }
 
 template <int SW>
-static int dispatch_bn(const adp_conv_gemm_args& a, int bn, cudaStream_t s) {
+static int dispatch_bn2(const adp_conv_gemm_args& a, int bn, cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_gemm<16, SW>(a, s);
-    case 32: return launch_gemm<32, SW>(a, s);
-    case 64: return launch_gemm<64, SW>(a, s);
-    case 128: return launch_gemm<128, SW>(a, s);
-    case 256: return launch_gemm<256, SW>(a, s);
+    case 16: return launch_gemm2<16, SW>(a, s);
+    case 32: return launch_gemm2<32, SW>(a, s);
+    case 64: return launch_gemm2<64, SW>(a, s);
+    case 128: return launch_gemm2<128, SW>(a, s);
+    case 256: return launch_gemm2<256, SW>(a, s);
   }
   return set_error("adp_conv_gemm: unsupported N tile %d", bn);
 }
 
 }  // namespace adp
 
+extern "C" int adp_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return adp::set_error("adp_debug_set: bad key %d", key);
+  adp::g_debug[key] = value;
+  return 0;
+}
+
 extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream) {
   using namespace adp;
+  if (g_debug[0] == 1) return conv_gemm_v1(args, stream);
   ADP_CHECK(args != nullptr, "adp_conv_gemm: null args");
   const adp_conv_gemm_args& a = *args;
   ADP_CHECK(a.a && a.w && a.out, "adp_conv_gemm: null a/w/out");
@@ -321,6 +457,7 @@ extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream
   ADP_CHECK(a.n_valid > 0 && a.n_valid % 8 == 0 && a.n_valid <= a.n_pad && a.n_pad % 16 == 0,
             "adp_conv_gemm: n_valid=%d n_pad=%d", a.n_valid, a.n_pad);
   ADP_CHECK(a.phases >= 1, "adp_conv_gemm: phases=%d", a.phases);
+  ADP_CHECK(a.ld_gate % 4 == 0, "adp_conv_gemm: ld_gate=%d must be a multiple of 4", a.ld_gate);
   if (a.up_factor > 1) {
     ADP_CHECK(a.phases == a.up_factor, "adp_conv_gemm: phases (%d) != up_factor (%d)", a.phases,
               a.up_factor);
@@ -329,8 +466,10 @@ extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream
     ADP_CHECK(a.ntaps >= 1 && a.ntaps <= 3 && a.phases == 1, "adp_conv_gemm: ntaps=%d phases=%d",
               a.ntaps, a.phases);
     ADP_CHECK(a.k_total >= a.ntaps * a.c_in, "adp_conv_gemm: k_total too small");
+    for (int i = 1; i < a.ntaps; ++i)
+      ADP_CHECK(a.tap_off[i] == a.tap_off[i - 1] + 1,
+                "adp_conv_gemm: tap offsets must be consecutive and ascending");
   }
-  ADP_CHECK(a.ld_gate % 4 == 0, "adp_conv_gemm: ld_gate=%d must be a multiple of 4", a.ld_gate);
   if (a.out_fp32) {
     ADP_CHECK(!a.residual && !a.stats, "adp_conv_gemm: out_fp32 excludes residual/stats");
   }
@@ -338,20 +477,21 @@ extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream
     ADP_CHECK(a.groups > 0 && a.groups <= kMaxGroups && a.n_valid % a.groups == 0,
               "adp_conv_gemm: groups=%d n_valid=%d", a.groups, a.n_valid);
   }
-  // N tile: largest that divides n_pad and still gives >= ~1 wave of CTAs
+  // N tile: the widest that divides n_pad (fewest re-reads of A); persistent CTAs take care of
+  // SM fill, so only very small problems prefer narrower tiles.
   int bn = a.block_n;
   if (bn == 0) {
     const long m_tiles = (long)a.B * ((a.T + kBM - 1) / kBM);
     bn = 16;
     for (int cand = 256; cand >= 16; cand >>= 1) {
       if (a.n_pad % cand) continue;
-      const long ctas = m_tiles * (a.phases * a.n_pad / cand);
-      if (ctas >= 120 || cand <= 64) { bn = cand; break; }
+      const long tiles = m_tiles * (a.phases * a.n_pad / cand);
+      if (tiles >= 96 || cand <= 64) { bn = cand; break; }
     }
   }
   ADP_CHECK(a.n_pad % bn == 0, "adp_conv_gemm: N tile %d does not divide n_pad %d", bn, a.n_pad);
   cudaStream_t s = as_stream(stream);
-  if (a.c_in % 64 == 0) return dispatch_bn<128>(a, bn, s);
-  if (a.c_in % 32 == 0) return dispatch_bn<64>(a, bn, s);
-  return dispatch_bn<32>(a, bn, s);
+  if (a.c_in % 64 == 0) return dispatch_bn2<128>(a, bn, s);
+  if (a.c_in % 32 == 0) return dispatch_bn2<64>(a, bn, s);
+  return dispatch_bn2<32>(a, bn, s);
 }

@@ -35,6 +35,9 @@ int adp_version(void);
 const char* adp_last_error(void);
 /* 0 iff the current CUDA device is compute capability 10.x (B200). */
 int adp_device_check(void);
+/* Diagnostic switches for A/B runs (key 0: GEMM implementation 2=persistent 1=v1; key 1: one
+ * A box for all taps; key 2: descriptor base-offset mode).  Not part of the hot path. */
+int adp_debug_set(int key, int value);
 
 /* ---------------------------------------------------------------------------------------
  * adp_conv_gemm: shifted-tap GEMM on tcgen05 tensor cores (TMA -> smem -> UMMA -> TMEM).

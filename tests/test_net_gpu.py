@@ -7,10 +7,10 @@ plus size-independent properties at the README (BASELINE) configuration.
 Stated bf16 tolerance (north_star: "stated bf16 tolerance"): storage is bf16 with fp32
 accumulation, so every activation carries ~2^-9 relative rounding.  The net output is
 v = x + gate*branch with |branch| << |x| at initialisation, so two metrics are bounded:
-  * rel-L2 error of v                      <= 1e-3   (the fp32 rtol of the north star)
-  * rel-L2 error of the branch (v - skip)  <= BRANCH_TOL = 3e-2
-    (the fp32 oracle evaluated under bf16 autocast on CPU differs from itself by 5.8e-3 on
-     the same metric -- stored in the golden file as bf16_err_branch)."""
+  * rel-L2 error of v                      <= 1e-4   (10x inside the north star's fp32 rtol)
+  * rel-L2 error of the branch (v - skip)  <= BRANCH_TOL = 1.2e-2 = 2x the error of the fp32
+    oracle itself evaluated under bf16 autocast on CPU (5.8e-3 on the same metric, stored
+    in the golden file as bf16_err_branch).  Measured on B200: 3.0e-3 (tiny), 4.4e-3 (README)."""
 import os
 
 import numpy as np
@@ -19,8 +19,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-BRANCH_TOL = 3e-2
-V_TOL = 1e-3
+BRANCH_TOL = 1.2e-2
+V_TOL = 1e-4
 
 TINY = dict(in_channels=2, channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2],
             attentions=[0, 0, 1], attention_heads=2, attention_features=64)
@@ -54,10 +54,10 @@ def t(a):
     return torch.from_numpy(np.asarray(a)).to(DEV)
 
 
-def check(v, v_ref, skip, what, branch_tol=BRANCH_TOL):
+def check(v, v_ref, skip, what, branch_tol=BRANCH_TOL, v_tol=V_TOL):
     e_v, e_b = rel_l2(v, v_ref), rel_l2(v.cpu() - skip.cpu(), v_ref.cpu() - skip.cpu())
     print(f"{what}: rel-L2(v) {e_v:.3e}  rel-L2(branch) {e_b:.3e}")
-    assert e_v <= V_TOL, f"{what}: v error {e_v:.3e} > {V_TOL}"
+    assert e_v <= v_tol, f"{what}: v error {e_v:.3e} > {v_tol}"
     assert e_b <= branch_tol, f"{what}: branch error {e_b:.3e} > {branch_tol}"
 
 
@@ -94,8 +94,9 @@ def test_text_cfg_vs_golden(adp, oracle_port, golden_dir):
     v1 = model.net(x, sigma, embedding=emb)
     check(v1, torch.from_numpy(g["v_scale1"]), x, "text-cond forward, scale 1")
     v5 = model.net(x, sigma, embedding=emb, embedding_scale=5.0)
-    # guidance extrapolates: v_m + 5 (v_c - v_m) amplifies the branch error by up to ~9x
-    check(v5, torch.from_numpy(g["v_scale5"]), x, "text-cond forward, CFG 5", branch_tol=0.15)
+    # guidance extrapolates: v_m + 5 (v_c - v_m) amplifies the error of both passes (|1-s|+|s| = 9x)
+    check(v5, torch.from_numpy(g["v_scale5"]), x, "text-cond forward, CFG 5", branch_tol=0.1,
+          v_tol=9e-4)
     s = model.sample(t(g["noise"]), num_steps=3, embedding=emb, embedding_scale=5.0)
     e = rel_l2(s, torch.from_numpy(g["sample3"]))
     print(f"CFG sampler 3 steps: rel-L2 {e:.3e}")
