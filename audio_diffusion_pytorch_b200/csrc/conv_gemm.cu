@@ -4,15 +4,19 @@
 // position): D[m = time position, n = output channel] = sum_{tap,k} A[m + off(tap), k] * W[n, tap, k]
 //   A: channels-last activations -> K-major operand.  ONE TMA box of (128 + span) rows per
 //      64-channel chunk serves all taps: tap j is the same smem tile read through a UMMA
-//      descriptor whose start address is advanced by j rows.  Rows outside [0,T) are
-//      zero-filled by TMA = the conv's zero padding.
-//   W: packed weights [N][taps*C_in] -> K-major operand, own smem ring (one box per tap+chunk).
+//      descriptor whose start address is advanced by j rows (the 128B swizzle is a function of
+//      the absolute smem address, so row-shifted starts need no re-layout).  Rows outside
+//      [0,T) are zero-filled by TMA = the conv's zero padding.
+//   W: packed weights [N][taps*C_in] -> K-major operand.
+//   A pipeline stage = KC chunks x {A box, one W box per tap} behind ONE full/empty mbarrier
+//      pair, so the single-thread issue loops pay one barrier round trip per KC*taps*4 MMAs.
 //   D: fp32 in TMEM, 128 lanes x BN columns, DOUBLE buffered: the epilogue of tile i drains
 //      buffer i&1 while the MMAs of tile i+1 fill the other one.
-// Persistent: grid = #SMs, CTA c walks tiles c, c+grid, ... (n fastest: the CTAs of one wave
-// share A tiles through L2).  Warp roles (192 threads): warp 0 TMA producer + TMEM allocator,
-// warp 1 MMA issuer, warps 2-5 epilogue (TMEM lane quarter = warp & 3).  The epilogue
-// prefetches the residual rows of its tile into registers while the tile's MMAs still run.
+// Persistent: each CTA owns a contiguous range of tiles (n fastest).  Warp roles (192 threads):
+// warp 0 TMA producer + TMEM allocator, warp 1 MMA issuer, warps 2-5 epilogue (TMEM lane
+// quarter = warp & 3).  The epilogue prefetches the residual rows of its tile into registers
+// while the tile's MMAs still run, and keeps GroupNorm partial sums in thread-private smem
+// slots (no shuffles / atomics per tile; one reduction per batch change).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -20,14 +24,13 @@ namespace adp {
 
 int conv_gemm_v1(const adp_conv_gemm_args* args, adp_stream_t stream);
 
-// debug / A-B switches (adp_debug_set): [0] impl 2=persistent 1=v1; [1] single A load for all
-// taps; [2] descriptor base_offset mode for row-shifted starts (0: zero, 1: (addr>>7)&7)
+// A/B + diagnostic switches (adp_debug_set): [0] impl 2=persistent 1=v1; [3] CTAs/SM override;
+// [4] bit0 skip MMAs, bit1 skip TMA loads (timing experiments only); [5] KC override
 int g_debug[8] = {2, 1, 0, 0, 0, 0, 0, 0};
 
 constexpr int kBM = 128;
-constexpr int kMaxNA = 4;
-constexpr int kMaxNW = 8;
-constexpr int kMaxGroups = 32;
+constexpr int kMaxStages = 8;
+constexpr int kMaxGroups = 8;      // GroupNorm groups handled by the fused statistics
 
 struct Gemm2Params {
   __nv_bfloat16* out;
@@ -37,26 +40,20 @@ struct Gemm2Params {
   double* stats;
   int T, tiles_per_batch, c_in, ldo;
   int n_pad, n_valid;
-  int ntaps, tap_off0, tap_off1, tap_off2, up_factor;
-  int groups, group_size;
+  int ntaps, tap_off0, up_factor;
+  int groups, group_size, group_shift;   // group_shift >= 0: group = ch >> shift
   int out_fp32, ld_gate;
-  int n_tiles_n, total_tiles;
-  int a_rows;        // rows per A box (128 + tap span) when single_load, else 128
-  int single_load;
-  int na, nw;        // ring depths
-  int a_stage_bytes, w_stage_bytes;
-  int base_off_mode;
+  int n_tiles_n, total_tiles, tiles_per_cta;
+  int a_rows;            // rows per A box = 128 + tap span
+  int kc;                // 64-channel chunks per stage
+  int k_stages;          // stages per tile = (c_in / BK) / kc
+  int n_stages;          // ring depth
+  int a_sub_bytes, w_sub_bytes, stage_bytes, max_taps;
+  int dbg;
 };
 
-template <int SW>
-__device__ __forceinline__ uint64_t desc_kmajor_shifted(uint32_t addr, int base_off_mode) {
-  uint64_t d = umma_desc_kmajor<SW>(addr);
-  if (base_off_mode) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
-  return d;
-}
-
 struct TileInfo {
-  int b, t0, n0, phase, ch0, ntaps, min_off, row0, row1, row2;
+  int b, t0, n0, phase, ch0, ntaps, min_off;
 };
 
 __device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, int BN) {
@@ -72,43 +69,61 @@ __device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, in
     if (ti.phase == 0) { ti.ntaps = 2; ti.min_off = -1; }
     else if (ti.phase == p.up_factor - 1) { ti.ntaps = 2; ti.min_off = 0; }
     else { ti.ntaps = 1; ti.min_off = 0; }
-    ti.row0 = 0; ti.row1 = 1; ti.row2 = 2;
   } else {
     ti.ntaps = p.ntaps;
     ti.min_off = p.tap_off0;
-    ti.row0 = 0; ti.row1 = p.tap_off1 - p.tap_off0; ti.row2 = p.tap_off2 - p.tap_off0;
   }
   return ti;
 }
 
+// thread-private GroupNorm partial sums: slot (value v of group g, epilogue thread et)
+struct StatSlots {
+  float* base;   // [2*kMaxGroups][128]
+  int et;
+  int cur_g;
+  float s, q;
+  __device__ __forceinline__ void flush() {
+    if (cur_g >= 0) {
+      base[(2 * cur_g) * 128 + et] += s;
+      base[(2 * cur_g + 1) * 128 + et] += q;
+    }
+    s = 0.f; q = 0.f;
+  }
+  __device__ __forceinline__ void add(float v, int g) {
+    if (g != cur_g) { flush(); cur_g = g; }
+    s += v; q += v * v;
+  }
+};
+
 template <int BN, int SW>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (BN <= 64 ? 3 : (BN <= 128 ? 2 : 1)))
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const Gemm2Params p) {
   constexpr int BK = SW / 2;
   constexpr int ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns per accumulator buffer
   constexpr int CH = BN < 32 ? 16 : 32;           // epilogue column chunk
+  constexpr uint32_t kWTapBytes = BN * SW;        // bytes one W box writes
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t a_full[kMaxNA], a_empty[kMaxNA];
-  __shared__ uint64_t w_full[kMaxNW], w_empty[kMaxNW];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_stats[2 * kMaxGroups];
+  __shared__ float s_part[2 * kMaxGroups * 128];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* a_ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* w_ring = a_ring + p.na * p.a_stage_bytes;
-  const int k_chunks = p.c_in / BK;
+  uint8_t* ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
 
-  if (threadIdx.x < 2 * kMaxGroups) s_stats[threadIdx.x] = 0.f;
+  const int tile_begin = blockIdx.x * p.tiles_per_cta;
+  int tile_end = tile_begin + p.tiles_per_cta;
+  if (tile_end > p.total_tiles) tile_end = p.total_tiles;
+
+  for (int i = threadIdx.x; i < 2 * kMaxGroups * 128; i += blockDim.x) s_part[i] = 0.f;
   if (warp == 0) {
     tmem_alloc(&tmem_slot, 2 * ACC_COLS);
     tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < p.nw; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -122,36 +137,28 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ---------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0;
+      int s = 0;
+      uint32_t ph = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * SW;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileInfo ti = tile_info(p, tile, BN);
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          if (p.single_load) {
-            const uint32_t sa = ia % p.na;
-            mbar_wait(&a_empty[sa], ((ia / p.na) & 1) ^ 1);
-            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-            tma_load_3d(a_ring + sa * p.a_stage_bytes, &tmA, &a_full[sa], kc * BK,
-                        ti.t0 + ti.min_off, ti.b);
-            ++ia;
-          }
-          for (int tap = 0; tap < ti.ntaps; ++tap) {
-            if (!p.single_load) {
-              const int row = tap == 0 ? ti.row0 : (tap == 1 ? ti.row1 : ti.row2);
-              const uint32_t sa = ia % p.na;
-              mbar_wait(&a_empty[sa], ((ia / p.na) & 1) ^ 1);
-              mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-              tma_load_3d(a_ring + sa * p.a_stage_bytes, &tmA, &a_full[sa], kc * BK,
-                          ti.t0 + ti.min_off + row, ti.b);
-              ++ia;
+        const uint32_t tx = static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes);
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = ring + s * p.stage_bytes;
+          if (p.dbg & 2) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], tx);
+            for (int c = 0; c < p.kc; ++c) {
+              const int k0 = (ks * p.kc + c) * BK;
+              tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
+              uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
+              for (int tap = 0; tap < ti.ntaps; ++tap)
+                tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
             }
-            const uint32_t sw = iw % p.nw;
-            mbar_wait(&w_empty[sw], ((iw / p.nw) & 1) ^ 1);
-            mbar_arrive_expect_tx(&w_full[sw], BN * SW);
-            tma_load_2d(w_ring + sw * p.w_stage_bytes, &tmW, &w_full[sw], tap * p.c_in + kc * BK,
-                        ti.n0);
-            ++iw;
           }
+          if (++s == p.n_stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -159,41 +166,41 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-      uint32_t ia = 0, iw = 0, j = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      // descriptor of the ring base; byte offsets are added to the 14-bit address field
+      const uint64_t desc0 = umma_desc_kmajor<SW>(smem_u32(ring));
+      const uint32_t stage_u = static_cast<uint32_t>(p.stage_bytes) >> 4;
+      const uint32_t a_sub_u = static_cast<uint32_t>(p.a_sub_bytes) >> 4;
+      const uint32_t w_sub_u = static_cast<uint32_t>(p.w_sub_bytes) >> 4;
+      const uint32_t w_base_u = static_cast<uint32_t>(p.kc) * a_sub_u;
+      int s = 0;
+      uint32_t ph = 0, j = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
         const TileInfo ti = tile_info(p, tile, BN);
         const uint32_t buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
         uint32_t accumulate = 0;
-        for (int kc = 0; kc < k_chunks; ++kc) {
-          uint32_t sa = ia % p.na;
-          if (p.single_load) mbar_wait(&a_full[sa], (ia / p.na) & 1);
-          for (int tap = 0; tap < ti.ntaps; ++tap) {
-            int row = 0;
-            if (p.single_load) {
-              row = tap == 0 ? ti.row0 : (tap == 1 ? ti.row1 : ti.row2);
-            } else {
-              sa = ia % p.na;
-              mbar_wait(&a_full[sa], (ia / p.na) & 1);
-            }
-            const uint32_t sw = iw % p.nw;
-            mbar_wait(&w_full[sw], (iw / p.nw) & 1);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_ring + sa * p.a_stage_bytes) + row * SW;
-            const uint32_t w_addr = smem_u32(w_ring + sw * p.w_stage_bytes);
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (!(p.dbg & 1)) {
+            const uint64_t sdesc = desc0 + static_cast<uint64_t>(s * stage_u);
+            for (int c = 0; c < p.kc; ++c) {
+              const uint64_t adesc = sdesc + c * a_sub_u;
+              const uint64_t wdesc = sdesc + w_base_u + c * p.max_taps * w_sub_u;
+              for (int tap = 0; tap < ti.ntaps; ++tap) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              umma_bf16(d_tmem, desc_kmajor_shifted<SW>(a_addr + kk * 32, p.base_off_mode),
-                        umma_desc_kmajor<SW>(w_addr + kk * 32), idesc, accumulate);
-              accumulate = 1;
+                for (int kk = 0; kk < BK / 16; ++kk) {
+                  umma_bf16(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
+                            wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
             }
-            umma_commit(&w_empty[sw]);
-            ++iw;
-            if (!p.single_load) { umma_commit(&a_empty[sa]); ++ia; }
           }
-          if (p.single_load) { umma_commit(&a_empty[sa]); ++ia; }
+          umma_commit(&empty_bar[s]);
+          if (++s == p.n_stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&acc_full[buf]);
       }
@@ -205,10 +212,26 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const bool do_stats = p.stats != nullptr;
     const int et = threadIdx.x - 64;        // 0..127 among epilogue threads
-    GroupStatAcc acc;
+    StatSlots acc{s_part, et, -1, 0.f, 0.f};
     int cur_b = -1;
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+
+    auto publish_stats = [&](int b_done) {   // all 128 epilogue threads
+      acc.flush();
+      acc.cur_g = -1;
+      named_bar_sync(1, 128);
+      if (et < 2 * p.groups) {
+        float tot = 0.f;
+        for (int i = 0; i < 128; ++i) tot += s_part[et * 128 + ((i + et) & 127)];
+        if (tot != 0.f)
+          atomicAdd(p.stats + static_cast<size_t>(b_done) * 2 * p.groups + et,
+                    static_cast<double>(tot));
+      }
+      named_bar_sync(1, 128);
+      for (int g2 = 0; g2 < 2 * p.groups; ++g2) s_part[g2 * 128 + et] = 0.f;
+    };
+
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
       const TileInfo ti = tile_info(p, tile, BN);
       const uint32_t buf = j & 1;
       const int t = ti.t0 + row;
@@ -216,19 +239,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const size_t row_off = (static_cast<size_t>(ti.b) * p.T + (row_ok ? t : 0)) * p.ldo +
                              static_cast<size_t>(ti.phase) * p.n_valid;
       if (do_stats && ti.b != cur_b) {
-        if (cur_b >= 0) {   // publish the finished batch's partial sums
-          acc.flush(s_stats, lane);
-          acc.cur_g = -1;
-          named_bar_sync(1, 128);
-          if (et < 2 * p.groups) {
-            const float val = s_stats[et];
-            if (val != 0.f)
-              atomicAdd(p.stats + static_cast<size_t>(cur_b) * 2 * p.groups + et,
-                        static_cast<double>(val));
-            s_stats[et] = 0.f;
-          }
-          named_bar_sync(1, 128);
-        }
+        if (cur_b >= 0) publish_stats(cur_b);
         cur_b = ti.b;
       }
       // residual rows of this tile -> registers, while the tile's MMAs are still running
@@ -302,8 +313,19 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int i = 0; i < 8; ++i) v[i] = 0.f;
           }
           if (do_stats) {
+            if (p.group_shift >= 3) {          // the whole 8-vector lies in one group
+              float s8 = 0.f, q8 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc.add(v[i], (ch + i) / p.group_size, s_stats, lane);
+              for (int i = 0; i < 8; ++i) { s8 += v[i]; q8 += v[i] * v[i]; }
+              const int g = ch >> p.group_shift;
+              if (g != acc.cur_g) { acc.flush(); acc.cur_g = g; }
+              acc.s += s8; acc.q += q8;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                acc.add(v[i], p.group_shift >= 0 ? (ch + i) >> p.group_shift
+                                                 : (ch + i) / p.group_size);
+            }
           }
         }
       }
@@ -312,16 +334,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (do_stats && cur_b >= 0) {
-      acc.flush(s_stats, lane);
-      named_bar_sync(1, 128);
-      if (et < 2 * p.groups) {
-        const float val = s_stats[et];
-        if (val != 0.f)
-          atomicAdd(p.stats + static_cast<size_t>(cur_b) * 2 * p.groups + et,
-                    static_cast<double>(val));
-      }
-    }
+    if (do_stats && cur_b >= 0) publish_stats(cur_b);
   }
 
   tc_fence_before();
@@ -349,25 +362,43 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   const int tiles_per_batch = (a.T + kBM - 1) / kBM;
   const bool up = a.up_factor > 1;
   const int max_taps = up ? 2 : a.ntaps;
-  const int span = up ? 1 : (a.ntaps > 1 ? a.tap_off[a.ntaps - 1] - a.tap_off[0] : 0);
-  const int single = (g_debug[1] != 0 && max_taps > 1) ? 1 : 0;
-  const int a_rows = single ? kBM + span : kBM;
+  const int span = up ? 1 : a.ntaps - 1;
+  const int a_rows = kBM + span;
   const int k_chunks = a.c_in / BK;
 
   Gemm2Params p;
-  p.a_stage_bytes = (a_rows * SW + 1023) / 1024 * 1024;
-  p.w_stage_bytes = (BN * SW + 1023) / 1024 * 1024;
-  // ring depths under ~196 KB: A boxes are reused by all taps, W boxes stream
-  const int a_iters = k_chunks * (single ? 1 : max_taps);
-  (void)a_iters;
-  int na = p.a_stage_bytes <= 9 * 1024 ? 4 : 3;   // the ring runs across tiles (persistent)
-  int nw = (196 * 1024 - na * p.a_stage_bytes) / p.w_stage_bytes;
-  if (nw > kMaxNW) nw = kMaxNW;
-  if (nw < 2) return set_error("adp_conv_gemm: tile does not fit shared memory");
-  p.na = na;
-  p.nw = nw;
-  const size_t smem = static_cast<size_t>(na) * p.a_stage_bytes +
-                      static_cast<size_t>(nw) * p.w_stage_bytes + 1024;
+  p.a_sub_bytes = (a_rows * SW + 1023) / 1024 * 1024;
+  p.w_sub_bytes = (BN * SW + 1023) / 1024 * 1024;
+  p.max_taps = max_taps;
+  const int chunk_bytes = p.a_sub_bytes + max_taps * p.w_sub_bytes;
+
+  // CTAs per SM: the epilogue (4 warps per CTA) is the critical resource of short-K tiles, so
+  // those run 2-3 CTAs per SM; long-K tiles want deep rings of fat stages instead.
+  const int w_iters = k_chunks * max_taps;
+  int occ = 1;
+  if (BN <= 64 && w_iters <= 8) occ = 3;
+  else if (BN <= 128 && w_iters <= 12) occ = 2;
+  if (g_debug[3] > 0) occ = g_debug[3];
+  const int tmem_occ = 512 / (2 * (BN < 32 ? 32 : BN));
+  if (occ > tmem_occ) occ = tmem_occ;
+  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? 100 : 62)) * 1024; };  // 8 KB static smem/CTA
+  while (occ > 1 && budget_of(occ) < 2 * chunk_bytes) --occ;   // need >= 2 stages in the ring
+  const int budget = budget_of(occ);
+  // chunks per stage: amortise one mbarrier round trip over >= 8 MMAs where smem allows
+  int kc = 1;
+  while (kc * 2 <= 4 && k_chunks % (kc * 2) == 0 && kc * max_taps * (BK / 16) < 8 &&
+         2 * (kc * 2) * chunk_bytes <= budget)
+    kc *= 2;
+  if (g_debug[5] > 0 && k_chunks % g_debug[5] == 0) kc = g_debug[5];
+  p.kc = kc;
+  p.k_stages = k_chunks / kc;
+  p.stage_bytes = kc * chunk_bytes;
+  int n_stages = budget / p.stage_bytes;
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  if (n_stages < 2)
+    return set_error("adp_conv_gemm: stage of %d bytes does not fit (BN=%d)", p.stage_bytes, BN);
+  p.n_stages = n_stages;
+  const size_t smem = static_cast<size_t>(n_stages) * p.stage_bytes + 1024;
 
   CUtensorMap tmA, tmW;
   {
@@ -403,20 +434,22 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   p.n_valid = a.n_valid;
   p.ntaps = a.ntaps;
   p.tap_off0 = a.tap_off[0];
-  p.tap_off1 = a.tap_off[1];
-  p.tap_off2 = a.tap_off[2];
   p.up_factor = a.up_factor;
   p.groups = a.stats ? a.groups : 0;
   p.group_size = a.stats ? a.n_valid / a.groups : 1;
+  p.group_shift = -1;
+  for (int sft = 0; sft < 16; ++sft)
+    if ((1 << sft) == p.group_size) p.group_shift = sft;
   p.out_fp32 = a.out_fp32;
   p.ld_gate = a.ld_gate > 0 ? a.ld_gate : a.n_valid;
   p.n_tiles_n = a.phases * a.n_pad / BN;
   p.total_tiles = a.B * tiles_per_batch * p.n_tiles_n;
   p.a_rows = a_rows;
-  p.single_load = single;
-  p.base_off_mode = g_debug[2];
+  p.dbg = g_debug[4];
 
-  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  int grid = p.total_tiles < occ * num_sms() ? p.total_tiles : occ * num_sms();
+  p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
+  grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   conv_gemm2_kernel<BN, SW><<<grid, 192, smem, stream>>>(tmA, tmW, p);
   ADP_LAUNCH_CHECK();
   return 0;
@@ -475,15 +508,16 @@ extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream
   }
   if (a.stats) {
     ADP_CHECK(a.groups > 0 && a.groups <= kMaxGroups && a.n_valid % a.groups == 0,
-              "adp_conv_gemm: groups=%d n_valid=%d", a.groups, a.n_valid);
+              "adp_conv_gemm: groups=%d n_valid=%d (fused statistics handle <= %d groups)",
+              a.groups, a.n_valid, kMaxGroups);
   }
-  // N tile: the widest that divides n_pad (fewest re-reads of A); persistent CTAs take care of
-  // SM fill, so only very small problems prefer narrower tiles.
+  // N tile: persistent CTAs take care of SM fill; prefer 128 (W traffic dominates either way
+  // and two accumulator buffers of 128 columns leave room for 2 CTAs/SM on short-K shapes)
   int bn = a.block_n;
   if (bn == 0) {
     const long m_tiles = (long)a.B * ((a.T + kBM - 1) / kBM);
     bn = 16;
-    for (int cand = 256; cand >= 16; cand >>= 1) {
+    for (int cand = 128; cand >= 16; cand >>= 1) {
       if (a.n_pad % cand) continue;
       const long tiles = m_tiles * (a.phases * a.n_pad / cand);
       if (tiles >= 96 || cand <= 64) { bn = cand; break; }
