@@ -7,6 +7,7 @@
 namespace adp {
 
 static thread_local char g_err[512] = "";
+int g_pdl = 1;
 
 int set_error(const char* fmt, ...) {
   va_list ap;

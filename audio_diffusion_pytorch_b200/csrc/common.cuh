@@ -34,4 +34,25 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 inline cudaStream_t as_stream(adp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Every kernel is launched with the programmatic-dependent-launch attribute: kernel N+1 may
+// start (set up smem / mbarriers / TMEM, prefetch tensor maps) while kernel N drains; it calls
+// griddepcontrol.wait before its first global-memory access.  adp_debug_set(6, 0) disables.
+extern int g_pdl;
+template <typename Kern, typename... Args>
+inline cudaError_t launch_k(Kern kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* ptrs[] = {(void*)&args...};
+  return cudaLaunchKernelExC(&cfg, (const void*)kernel, ptrs);
+}
+
 }  // namespace adp

@@ -109,6 +109,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[2 * kMaxGroups * 128];
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
@@ -133,6 +134,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();   // inputs (activations, statistics, conditioning) come from the previous kernel
 
   if (warp == 0) {
     // ---------------------------------------------------------------------- TMA producer
@@ -450,7 +452,7 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   int grid = p.total_tiles < occ * num_sms() ? p.total_tiles : occ * num_sms();
   p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  conv_gemm2_kernel<BN, SW><<<grid, 192, smem, stream>>>(tmA, tmW, p);
+  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW>, dim3(grid), dim3(192), smem, stream, tmA, tmW, p));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -472,6 +474,7 @@ static int dispatch_bn2(const adp_conv_gemm_args& a, int bn, cudaStream_t s) {
 extern "C" int adp_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return adp::set_error("adp_debug_set: bad key %d", key);
   adp::g_debug[key] = value;
+  if (key == 6) adp::g_pdl = value;
   return 0;
 }
 

@@ -201,6 +201,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream may begin launching once every CTA of this
+// grid has executed it (or exited).  wait: block until the previous grid has completed and its
+// memory is visible -- must precede this kernel's first global-memory access.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // -------------------------------------------------------------------------------- misc
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) {

@@ -11,10 +11,13 @@ constexpr int kMaxC = 2048;
 
 // --------------------------------------------------------------------------- gn_silu
 // y = silu(x * a[b,c] + d[b,c]),  a = gamma*rstd, d = beta - mean*a  from (sum, sumsq).
+// Each CTA streams tiles of 1024 vectors, four independent 16-byte loads in flight per thread.
 __global__ void __launch_bounds__(256)
 gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                const float* __restrict__ gamma, const float* __restrict__ beta, int T, int C,
                int groups, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_a[kMaxC];
   __shared__ float s_d[kMaxC];
   const int b = blockIdx.y;
@@ -24,11 +27,9 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
     const int g = c / gsz;
     const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
     const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
-    const double mean = s * inv_n;
-    double var = q * inv_n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float a = gamma[c] * rstd;
+    const double mean = s * inv_n;                      // fp64 only where cancellation bites
+    const float var = fmaxf(static_cast<float>(q * inv_n - mean * mean), 0.f);
+    const float a = gamma[c] * rsqrtf(var + eps);
     s_a[c] = a;
     s_d[c] = beta[c] - static_cast<float>(mean) * a;
   }
@@ -37,20 +38,30 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
   const size_t nvec = static_cast<size_t>(T) * vpr;
   const uint4* xb = x + static_cast<size_t>(b) * nvec;
   uint4* yb = y + static_cast<size_t>(b) * nvec;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % vpr) << 3;
-    const uint4 u = __ldg(xb + i);
-    const uint32_t in[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+  for (size_t base = static_cast<size_t>(blockIdx.x) * 1024; base < nvec;
+       base += static_cast<size_t>(gridDim.x) * 1024) {
+    uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16(in[j]);
-      const float v0 = silu_f(f.x * s_a[c + 2 * j] + s_d[c + 2 * j]);
-      const float v1 = silu_f(f.y * s_a[c + 2 * j + 1] + s_d[c + 2 * j + 1]);
-      o[j] = pack_bf16(v0, v1);
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = base + k * 256 + threadIdx.x;
+      u[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
     }
-    yb[i] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = base + k * 256 + threadIdx.x;
+      if (i >= nvec) continue;
+      const int c = static_cast<int>(i % vpr) << 3;
+      const uint32_t in[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(in[j]);
+        const float v0 = silu_f(f.x * s_a[c + 2 * j] + s_d[c + 2 * j]);
+        const float v1 = silu_f(f.y * s_a[c + 2 * j + 1] + s_d[c + 2 * j + 1]);
+        o[j] = pack_bf16(v0, v1);
+      }
+      yb[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -58,6 +69,8 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int T, int C,
                 int groups) {
+  pdl_launch_dependents();
+  pdl_wait();
   // each thread keeps a fixed channel-vector (stride is a multiple of vectors-per-row)
   __shared__ float s_acc[2 * 64];
   const int b = blockIdx.y;
@@ -100,36 +113,35 @@ gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int T, 
 }
 
 // --------------------------------------------------------------------------- ln_film
-// One row = C channels = C/8 vectors spread over LPR lanes (VPL vectors per lane).
-template <int VPL, bool PER_CH>
+// One row = C channels = C/8 vectors spread over LPR lanes (VPL vectors per lane); UNR
+// independent row groups per warp iteration keep several 16-byte loads in flight per lane.
+constexpr int kMaxLnC = 1024;
+template <int VPL, bool PER_CH, int UNR>
 __global__ void __launch_bounds__(256)
 ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ ss,
                int ss_stride, double* __restrict__ stats, int T, int C, int lpr, int groups,
                float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float s_acc[2 * 64];
+  __shared__ __align__(16) float s_fs[kMaxLnC];
+  __shared__ __align__(16) float s_ft[kMaxLnC];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int rpw = 32 / lpr;          // rows per warp per iteration
+  const int rpw = 32 / lpr;          // rows per warp per group
   const int sub = lane / lpr;        // which of those rows
   const int l = lane - sub * lpr;    // lane inside the row
   const int vpr = C >> 3;
   const int gsz = groups > 0 ? C / groups : C;
   const bool do_stats = stats != nullptr;
   if (threadIdx.x < 128) s_acc[threadIdx.x] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // FiLM coefficients of this batch row
+    s_fs[c] = ss ? 1.f + ss[static_cast<size_t>(b) * ss_stride + c] : 1.f;
+    s_ft[c] = ss ? ss[static_cast<size_t>(b) * ss_stride + C + c] : 0.f;
+  }
   __syncthreads();
 
-  // FiLM coefficients of this lane's channels (fixed for the whole kernel)
-  float fs[VPL][8], ft[VPL][8];
-#pragma unroll
-  for (int it = 0; it < VPL; ++it) {
-    const int c = (it * lpr + l) << 3;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      fs[it][j] = ss ? 1.f + ss[static_cast<size_t>(b) * ss_stride + c + j] : 1.f;
-      ft[it][j] = ss ? ss[static_cast<size_t>(b) * ss_stride + C + c + j] : 0.f;
-    }
-  }
   constexpr int NACC = PER_CH ? 8 : VPL;
   float as[NACC], aq[NACC];
 #pragma unroll
@@ -139,73 +151,100 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
   uint4* yb = y + static_cast<size_t>(b) * T * vpr;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.f / static_cast<float>(C);
-  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * rpw; base < T;
-       base += warps_total * rpw) {
-    const int row = base + sub;
-    const bool ok = row < T;
-    float v[VPL][8];
-    float sum = 0.f;
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * rpw * UNR; base < T;
+       base += warps_total * rpw * UNR) {
+    uint4 u[UNR][VPL];
 #pragma unroll
-    for (int it = 0; it < VPL; ++it) {
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (ok) u = __ldg(xb + static_cast<size_t>(row) * vpr + it * lpr + l);
-      const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+    for (int un = 0; un < UNR; ++un) {
+      const int row = base + un * rpw + sub;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(in[j]);
-        v[it][2 * j] = f.x; v[it][2 * j + 1] = f.y;
-        sum += f.x + f.y;
+      for (int it = 0; it < VPL; ++it) {
+        u[un][it] = make_uint4(0, 0, 0, 0);
+        if (row < T) u[un][it] = __ldg(xb + static_cast<size_t>(row) * vpr + it * lpr + l);
       }
     }
-    for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * inv_c;
-    float sq = 0.f;
 #pragma unroll
-    for (int it = 0; it < VPL; ++it)
+    for (int un = 0; un < UNR; ++un) {
+      const int row = base + un * rpw + sub;
+      const bool ok = row < T;
+      float v[VPL][8];
+      float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean; sq += d * d; }
-    for (int o = lpr >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * inv_c + eps);
+      for (int it = 0; it < VPL; ++it) {
+        const uint32_t in[4] = {u[un][it].x, u[un][it].y, u[un][it].z, u[un][it].w};
 #pragma unroll
-    for (int it = 0; it < VPL; ++it) {
-      uint32_t o4[4];
-      float r[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float y0 = (v[it][2 * j] - mean) * rstd * fs[it][2 * j] + ft[it][2 * j];
-        const float y1 = (v[it][2 * j + 1] - mean) * rstd * fs[it][2 * j + 1] + ft[it][2 * j + 1];
-        o4[j] = pack_bf16(y0, y1);
-        const float2 rr = unpack_bf16(o4[j]);   // statistics of what is stored
-        r[2 * j] = rr.x; r[2 * j + 1] = rr.y;
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(in[j]);
+          v[it][2 * j] = f.x; v[it][2 * j + 1] = f.y;
+          sum += f.x + f.y;
+        }
       }
-      if (ok) {
-        yb[static_cast<size_t>(row) * vpr + it * lpr + l] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-        if (do_stats) {
-          if constexpr (PER_CH) {
+      for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * inv_c;
+      float sq = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { as[j] += r[j]; aq[j] += r[j] * r[j]; }
-          } else {
+      for (int it = 0; it < VPL; ++it)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { as[it] += r[j]; aq[it] += r[j] * r[j]; }
+        for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean; sq += d * d; }
+      for (int o = lpr >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * inv_c + eps);
+#pragma unroll
+      for (int it = 0; it < VPL; ++it) {
+        const int c = (it * lpr + l) << 3;
+        const float4 f0 = *reinterpret_cast<const float4*>(&s_fs[c]);
+        const float4 f1 = *reinterpret_cast<const float4*>(&s_fs[c + 4]);
+        const float4 t0 = *reinterpret_cast<const float4*>(&s_ft[c]);
+        const float4 t1 = *reinterpret_cast<const float4*>(&s_ft[c + 4]);
+        const float fs[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        const float ft[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+        uint32_t o4[4];
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float y0 = (v[it][2 * j] - mean) * rstd * fs[2 * j] + ft[2 * j];
+          const float y1 = (v[it][2 * j + 1] - mean) * rstd * fs[2 * j + 1] + ft[2 * j + 1];
+          o4[j] = pack_bf16(y0, y1);
+          const float2 rr = unpack_bf16(o4[j]);   // statistics of what is stored
+          r[2 * j] = rr.x; r[2 * j + 1] = rr.y;
+        }
+        if (ok) {
+          yb[static_cast<size_t>(row) * vpr + it * lpr + l] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          if (do_stats) {
+            if constexpr (PER_CH) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { as[j] += r[j]; aq[j] += r[j] * r[j]; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { as[it] += r[j]; aq[it] += r[j] * r[j]; }
+            }
           }
         }
       }
     }
   }
   if (do_stats) {
-    if constexpr (PER_CH) {
+    // lanes l, l+lpr, l+2*lpr, ... hold the same channels: fold them before touching smem
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = ((l << 3) + j) / gsz;
-        atomicAdd(&s_acc[2 * g], as[j]);
-        atomicAdd(&s_acc[2 * g + 1], aq[j]);
+    for (int j = 0; j < NACC; ++j)
+      for (int o = lpr; o < 32; o <<= 1) {
+        as[j] += __shfl_xor_sync(0xffffffffu, as[j], o);
+        aq[j] += __shfl_xor_sync(0xffffffffu, aq[j], o);
       }
-    } else {
+    if (sub == 0) {
+      if constexpr (PER_CH) {
 #pragma unroll
-      for (int it = 0; it < VPL; ++it) {
-        const int g = ((it * lpr + l) << 3) / gsz;
-        atomicAdd(&s_acc[2 * g], as[it]);
-        atomicAdd(&s_acc[2 * g + 1], aq[it]);
+        for (int j = 0; j < 8; ++j) {
+          const int g = ((l << 3) + j) / gsz;
+          atomicAdd(&s_acc[2 * g], as[j]);
+          atomicAdd(&s_acc[2 * g + 1], aq[j]);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < VPL; ++it) {
+          const int g = ((it * lpr + l) << 3) / gsz;
+          atomicAdd(&s_acc[2 * g], as[it]);
+          atomicAdd(&s_acc[2 * g + 1], aq[it]);
+        }
       }
     }
     __syncthreads();
@@ -228,6 +267,8 @@ __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                      const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N,
                      int ldx, int ldw, int ldy, int in_act, int out_act) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_x[];  // [16][K]
   const int b0 = blockIdx.y * kSkinnyRows;
   for (int i = threadIdx.x; i < kSkinnyRows * K; i += blockDim.x) {
@@ -284,6 +325,8 @@ skinny_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
 __global__ void time_features_kernel(const float* __restrict__ sigma,
                                      const float* __restrict__ freqs, float* __restrict__ out,
                                      int B, int nfreq, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const float s = sigma[b];
   for (int j = threadIdx.x; j < ld_out; j += blockDim.x) {
@@ -299,6 +342,8 @@ __global__ void time_features_kernel(const float* __restrict__ sigma,
 __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __restrict__ v,
                                     const float* __restrict__ ab, float* __restrict__ xn,
                                     int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float a0 = ab[0], b0 = ab[1], a1 = ab[2], b1 = ab[3];
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -311,6 +356,8 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                  int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16(silu_f(x[i]));
@@ -334,9 +381,10 @@ extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const fl
   ADP_CHECK(C % 8 == 0 && C <= kMaxC && groups > 0 && C % groups == 0,
             "adp_gn_silu: C=%d groups=%d unsupported", C, groups);
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
-  dim3 grid(pick_grid(nvec, 256 * 4, 148 * 16 / (B < 16 ? B : 16) + 1), B);
-  gn_silu_kernel<<<grid, 256, 0, as_stream(stream)>>>(
-      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta, T, C, groups, eps);
+  dim3 grid(pick_grid(nvec, 1024, 148 * 16 / (B < 16 ? B : 16) + 1), B);
+  ADP_CUDA(launch_k(gn_silu_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
+                    static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
+                    (int)T, (int)C, (int)groups, eps));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -348,8 +396,8 @@ extern "C" int adp_gn_stats(const void* x, double* stats, int32_t B, int32_t T, 
             "adp_gn_stats: C=%d groups=%d unsupported", C, groups);
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
   dim3 grid(pick_grid(nvec, 256 * 8, 148 * 8 / (B < 8 ? B : 8) + 1), B);
-  gn_stats_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint4*>(x), stats, T, C,
-                                                       groups);
+  ADP_CUDA(launch_k(gn_stats_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
+                    static_cast<const uint4*>(x), stats, (int)T, (int)C, (int)groups));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -376,14 +424,17 @@ extern "C" int adp_ln_film(const void* x, void* y, const float* scale_shift, int
     per_ch = gsz < 8;
     ADP_CHECK(per_ch ? (vpl == 1) : (gsz % 8 == 0), "adp_ln_film: group size %d unsupported", gsz);
   }
-  const int rows_per_block = 8 * (32 / lpr);
-  dim3 grid(pick_grid(T, rows_per_block * 4, 148 * 8 / (B < 8 ? B : 8) + 1), B);
+  ADP_CHECK(C <= kMaxLnC, "adp_ln_film: C=%d > %d", C, kMaxLnC);
+  const int unr = vpl <= 2 ? 2 : 1;
+  const int rows_per_block = 8 * (32 / lpr) * unr;
+  dim3 grid(pick_grid(T, rows_per_block * 2, 148 * 16 / (B < 16 ? B : 16) + 1), B);
   const uint4* xi = static_cast<const uint4*>(x);
   uint4* yo = static_cast<uint4*>(y);
   cudaStream_t s = as_stream(stream);
 #define ADP_LN(VPL, PC)                                                                         \
-  ln_film_kernel<VPL, PC><<<grid, 256, 0, s>>>(xi, yo, scale_shift, ss_stride, stats_out, T, C, \
-                                               lpr, groups, eps)
+  ADP_CUDA(launch_k(ln_film_kernel<VPL, PC, (VPL <= 2 ? 2 : 1)>, grid, dim3(256), (size_t)0, s, \
+                    xi, yo, scale_shift, (int)ss_stride, stats_out, (int)T, (int)C, (int)lpr,   \
+                    (int)groups, eps))
   if (per_ch) ADP_LN(1, true);
   else if (vpl == 1) ADP_LN(1, false);
   else if (vpl == 2) ADP_LN(2, false);
@@ -409,8 +460,9 @@ extern "C" int adp_skinny_linear(const float* x, const void* w, const float* bia
     smem_attr = smem;
   }
   dim3 grid(pick_grid(N, 8, 148 * 2), (B + kSkinnyRows - 1) / kSkinnyRows);
-  skinny_linear_kernel<<<grid, 256, smem, as_stream(stream)>>>(
-      x, static_cast<const __nv_bfloat16*>(w), bias, y, B, K, N, ldx, ldw, ldy, in_act, out_act);
+  ADP_CUDA(launch_k(skinny_linear_kernel, grid, dim3(256), smem, as_stream(stream), x,
+                    static_cast<const __nv_bfloat16*>(w), bias, y, (int)B, (int)K, (int)N, (int)ldx,
+                    (int)ldw, (int)ldy, (int)in_act, (int)out_act));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -418,15 +470,16 @@ extern "C" int adp_skinny_linear(const float* x, const void* w, const float* bia
 extern "C" int adp_time_features(const float* sigma, const float* freqs, float* out, int32_t B,
                                  int32_t nfreq, int32_t ld_out, adp_stream_t stream) {
   ADP_CHECK(sigma && freqs && out && ld_out >= 2 * nfreq + 1, "adp_time_features: bad args");
-  time_features_kernel<<<B, 128, 0, as_stream(stream)>>>(sigma, freqs, out, B, nfreq, ld_out);
+  ADP_CUDA(launch_k(time_features_kernel, dim3(B), dim3(128), (size_t)0, as_stream(stream), sigma,
+                    freqs, out, (int)B, (int)nfreq, (int)ld_out));
   ADP_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t stream) {
   ADP_CHECK(x && y && n > 0, "adp_silu_bf16: bad args");
-  silu_bf16_kernel<<<pick_grid(static_cast<size_t>(n), 256, 148 * 4), 256, 0, as_stream(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(y), n);
+  ADP_CUDA(launch_k(silu_bf16_kernel, dim3(pick_grid(static_cast<size_t>(n), 256, 148 * 4)),
+                    dim3(256), (size_t)0, as_stream(stream), x, static_cast<__nv_bfloat16*>(y), n));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -434,8 +487,8 @@ extern "C" int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t st
 extern "C" int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_next,
                                 int64_t n, adp_stream_t stream) {
   ADP_CHECK(x && v && ab && x_next && n > 0, "adp_sampler_step: bad args");
-  sampler_step_kernel<<<pick_grid(static_cast<size_t>(n), 256 * 4, 148 * 8), 256, 0,
-                        as_stream(stream)>>>(x, v, ab, x_next, n);
+  ADP_CUDA(launch_k(sampler_step_kernel, dim3(pick_grid(static_cast<size_t>(n), 256 * 4, 148 * 8)),
+                    dim3(256), (size_t)0, as_stream(stream), x, v, ab, x_next, n));
   ADP_LAUNCH_CHECK();
   return 0;
 }

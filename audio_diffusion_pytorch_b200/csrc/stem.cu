@@ -13,6 +13,8 @@ constexpr int kStemMaxCo = 4;
 
 // ------------------------------------------------------------------------------ stem_in
 __global__ void __launch_bounds__(256) stem_in_kernel(const adp_stem_in_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];            // [c0][ci_total] then bias[c0]
   __shared__ float s_stats[2 * 64];
   const int cin = a.cx + a.ca;
@@ -124,6 +126,8 @@ __device__ __forceinline__ void stem_out_conv(const __nv_bfloat16* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) stem_out_kernel(const adp_stem_out_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ldg = a.ld_gate > 0 ? a.ld_gate : a.co;
   extern __shared__ float s_w[];   // conv w [co][3][c0], bias[co], adapt w [co][cin], adapt b[co]
   __shared__ double s_loss[8];
@@ -228,6 +232,8 @@ __global__ void __launch_bounds__(256) stem_out_kernel(const adp_stem_out_args a
 // -------------------------------------------------------------------------- narrow_conv
 template <int C>
 __global__ void __launch_bounds__(256) narrow_conv_kernel(const adp_narrow_conv_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int TB = 256;
   __shared__ __align__(16) float s_in[(TB + 2) * C];
   __shared__ __align__(16) float s_w[3 * C * C];   // [k][ci][co]
@@ -371,7 +377,7 @@ extern "C" int adp_stem_in(const adp_stem_in_args* args, adp_stream_t stream) {
   if (a.stats) ADP_CHECK(a.groups > 0 && a.groups <= 64 && a.c0 % a.groups == 0, "adp_stem_in: groups");
   const size_t smem = (static_cast<size_t>(a.c0) * (a.cx + a.ca) * a.f + a.c0) * sizeof(float);
   dim3 grid((a.T / a.f + 255) / 256, a.B);
-  stem_in_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
+  ADP_CUDA(launch_k(stem_in_kernel, grid, dim3(256), smem, as_stream(stream), a));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -390,7 +396,7 @@ extern "C" int adp_stem_out(const adp_stem_out_args* args, adp_stream_t stream) 
   const size_t smem =
       (static_cast<size_t>(a.co) * 3 * a.c0 + 2 * a.co + a.co * (a.cx + a.ca)) * sizeof(float);
   dim3 grid((a.T + 255) / 256, a.B);
-  stem_out_kernel<<<grid, 256, smem, as_stream(stream)>>>(a);
+  ADP_CUDA(launch_k(stem_out_kernel, grid, dim3(256), smem, as_stream(stream), a));
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -403,7 +409,7 @@ extern "C" int adp_narrow_conv(const adp_narrow_conv_args* args, adp_stream_t st
             a.C);
   ADP_CHECK(a.groups > 0 && a.C % a.groups == 0, "adp_narrow_conv: groups=%d", a.groups);
   dim3 grid((a.T + 255) / 256, a.B);
-  narrow_conv_kernel<8><<<grid, 256, 0, as_stream(stream)>>>(a);
+  ADP_CUDA(launch_k(narrow_conv_kernel<8>, grid, dim3(256), (size_t)0, as_stream(stream), a));
   ADP_LAUNCH_CHECK();
   return 0;
 }
