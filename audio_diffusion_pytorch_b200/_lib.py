@@ -41,6 +41,32 @@ class NarrowConvArgs(C.Structure):
                 ("gn_eps", f32), ("ln_eps", f32)]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [("g", vp), ("x", vp), ("dw", vp), ("B", i32), ("T", i32), ("n", i32), ("k", i32),
+                ("ldg", i32), ("ldx", i32), ("ldw", i32), ("g_cols", i32), ("x_cols", i32),
+                ("g_col0", i32), ("x_col0", i32), ("off", i32)]
+
+
+class NarrowConvBwdArgs(C.Structure):
+    _fields_ = [("dy", vp), ("x", vp), ("stats_in", vp), ("gamma", vp), ("beta", vp), ("w", vp),
+                ("dxh", vp), ("dgamma", vp), ("dbeta", vp), ("S", vp), ("dw", vp), ("dbias", vp),
+                ("B", i32), ("T", i32), ("C", i32), ("groups", i32), ("gn_eps", f32)]
+
+
+class StemOutBwdArgs(C.Structure):
+    _fields_ = [("dv", vp), ("gscale", vp), ("h", vp), ("x", vp), ("append", vp), ("noise", vp),
+                ("alpha", vp), ("beta", vp), ("w", vp), ("bias", vp), ("w_adapt", vp), ("gate", vp),
+                ("dh", vp), ("dw", vp), ("dbias", vp), ("dgate", vp), ("dw_adapt", vp),
+                ("db_adapt", vp), ("B", i32), ("T", i32), ("cx", i32), ("ca", i32), ("c0", i32),
+                ("co", i32), ("f", i32), ("ld_gate", i32), ("ld_dgate", i32)]
+
+
+class StemInBwdArgs(C.Structure):
+    _fields_ = [("dout", vp), ("x", vp), ("append", vp), ("noise", vp), ("alpha", vp), ("beta", vp),
+                ("dw", vp), ("dbias", vp), ("B", i32), ("T", i32), ("cx", i32), ("ca", i32),
+                ("c0", i32), ("f", i32)]
+
+
 _lib = None
 
 
@@ -71,6 +97,17 @@ def lib() -> C.CDLL:
         "adp_narrow_conv": [C.POINTER(NarrowConvArgs), vp],
         "adp_sampler_step": [vp, vp, vp, vp, C.c_int64, vp],
         "adp_silu_bf16": [vp, vp, C.c_int64, vp],
+        "adp_wgrad": [C.POINTER(WgradArgs), vp],
+        "adp_gn_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "adp_gn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "adp_ln_film_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, vp],
+        "adp_colsum": [vp, vp, i32, vp, i32, i32, i32, vp],
+        "adp_skip_gate": [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
+        "adp_skip_gate_bwd": [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
+        "adp_cond_bwd": [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "adp_narrow_conv_bwd": [C.POINTER(NarrowConvBwdArgs), vp],
+        "adp_stem_out_bwd": [C.POINTER(StemOutBwdArgs), vp],
+        "adp_stem_in_bwd": [C.POINTER(StemInBwdArgs), vp],
     }
     for name, argtypes in sig.items():
         if hasattr(L, name):
@@ -89,4 +126,7 @@ def check(rc: int, what: str) -> None:
 EXPORTS = ["adp_version", "adp_last_error", "adp_device_check", "adp_conv_gemm", "adp_gn_silu",
            "adp_gn_stats", "adp_ln_film", "adp_attention", "adp_skinny_linear",
            "adp_time_features", "adp_stem_in", "adp_stem_out", "adp_narrow_conv",
-           "adp_sampler_step", "adp_silu_bf16", "adp_debug_set"]
+           "adp_sampler_step", "adp_silu_bf16", "adp_debug_set", "adp_wgrad", "adp_gn_silu_bwd",
+           "adp_gn_bwd_apply", "adp_ln_film_bwd", "adp_colsum", "adp_skip_gate",
+           "adp_skip_gate_bwd", "adp_cond_bwd", "adp_narrow_conv_bwd", "adp_stem_out_bwd",
+           "adp_stem_in_bwd"]

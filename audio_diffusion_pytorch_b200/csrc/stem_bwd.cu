@@ -1,0 +1,375 @@
+// Backward of the network-boundary / narrow-level kernels of stem.cu (CUDA cores).
+// Pattern: stage the tile's activations and output gradients in shared memory, then
+//   (1) one thread per position for the data gradient, (2) one thread per parameter for the
+//   weight gradient (a 256-step dot product out of smem), one atomic per parameter per CTA.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace adp {
+
+constexpr int kTB = 256;
+
+// ---------------------------------------------------------------------- narrow_conv_bwd
+// forward: y = conv3(a) + bias, a = silu(xhat*gamma + beta), C == 8.  Given dy:
+//   dxh = (conv3^T dy) * silu'(z) * gamma  (first GroupNorm-backward pass, see adp_gn_bwd_apply)
+//   dgamma, dbeta, S[b,g] = (sum dxh, sum dxh*xhat), dw[co][ci][k], dbias[co].
+template <int C>
+__global__ void __launch_bounds__(kTB)
+narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(16) float s_a[(kTB + 2) * C];    // activated input, rows t0-1 .. t0+TB
+  __shared__ __align__(16) float s_dy[(kTB + 2) * C];   // output gradient, same rows
+  __shared__ __align__(16) float s_w[3 * C * C];        // [k][co][ci]
+  __shared__ float s_ga[C], s_be[C], s_mean[C], s_rstd[C];
+  __shared__ float s_red[4 * C];                        // dgamma, dbeta, S1, S2 per channel
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kTB;
+  for (int i = threadIdx.x; i < 3 * C * C; i += kTB) {
+    const int k = i / (C * C), r = i - k * C * C, co = r / C, ci = r - co * C;
+    s_w[i] = a.w[(co * C + ci) * 3 + k];
+  }
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x, gsz = C / a.groups, g = c / gsz;
+    const double inv_n = 1.0 / (static_cast<double>(gsz) * a.T);
+    const double mean = a.stats_in[(static_cast<size_t>(b) * a.groups + g) * 2] * inv_n;
+    const float var = fmaxf(static_cast<float>(
+        a.stats_in[(static_cast<size_t>(b) * a.groups + g) * 2 + 1] * inv_n - mean * mean), 0.f);
+    s_mean[c] = static_cast<float>(mean);
+    s_rstd[c] = rsqrtf(var + a.gn_eps);
+    s_ga[c] = a.gamma[c];
+    s_be[c] = a.beta[c];
+  }
+  if (threadIdx.x < 4 * C) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(a.x) + static_cast<size_t>(b) * a.T * C;
+  const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(a.dy) + static_cast<size_t>(b) * a.T * C;
+  for (int i = threadIdx.x; i < kTB + 2; i += kTB) {
+    const int t = t0 - 1 + i;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { s_a[i * C + c] = 0.f; s_dy[i * C + c] = 0.f; }
+    if (t >= 0 && t < a.T) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float xh = (__bfloat162float(xb[static_cast<size_t>(t) * C + c]) - s_mean[c]) * s_rstd[c];
+        s_a[i * C + c] = silu_f(xh * s_ga[c] + s_be[c]);
+        s_dy[i * C + c] = __bfloat162float(dyb[static_cast<size_t>(t) * C + c]);
+      }
+    }
+  }
+  __syncthreads();
+  // (1) data gradient, one thread per position
+  const int t = t0 + threadIdx.x;
+  float r_dg[C], r_db[C], r_s1[C], r_s2[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { r_dg[c] = 0.f; r_db[c] = 0.f; r_s1[c] = 0.f; r_s2[c] = 0.f; }
+  if (t < a.T) {
+    float da[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) da[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* dyr = &s_dy[(threadIdx.x + 2 - k) * C];     // dy[t - (k-1)]
+#pragma unroll
+      for (int co = 0; co < C; ++co) {
+        const float g = dyr[co];
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) da[ci] += g * s_w[(k * C + co) * C + ci];
+      }
+    }
+    float o[C], xh[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      xh[c] = (__bfloat162float(xb[static_cast<size_t>(t) * C + c]) - s_mean[c]) * s_rstd[c];
+      const float z = xh[c] * s_ga[c] + s_be[c];
+      const float sg = 1.f / (1.f + __expf(-z));
+      const float dz = da[c] * sg * (1.f + z * (1.f - sg));
+      o[c] = dz * s_ga[c];
+      r_dg[c] = dz * xh[c];
+      r_db[c] = dz;
+    }
+    __nv_bfloat16* op = static_cast<__nv_bfloat16*>(a.dxh) + (static_cast<size_t>(b) * a.T + t) * C;
+#pragma unroll
+    for (int c = 0; c < C; c += 8) {
+      const uint4 ov = make_uint4(pack_bf16(o[c], o[c + 1]), pack_bf16(o[c + 2], o[c + 3]),
+                                  pack_bf16(o[c + 4], o[c + 5]), pack_bf16(o[c + 6], o[c + 7]));
+      *reinterpret_cast<uint4*>(op + c) = ov;
+      const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {          // sums of the ROUNDED values the second pass reads
+        const float2 r = unpack_bf16(ou[j]);
+        r_s1[c + 2 * j] = r.x; r_s2[c + 2 * j] = r.x * xh[c + 2 * j];
+        r_s1[c + 2 * j + 1] = r.y; r_s2[c + 2 * j + 1] = r.y * xh[c + 2 * j + 1];
+      }
+    }
+  }
+  {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v0 = warp_sum(r_dg[c]), v1 = warp_sum(r_db[c]);
+      const float v2 = warp_sum(r_s1[c]), v3 = warp_sum(r_s2[c]);
+      if (lane == 0) {
+        atomicAdd(&s_red[c], v0); atomicAdd(&s_red[C + c], v1);
+        atomicAdd(&s_red[2 * C + c], v2); atomicAdd(&s_red[3 * C + c], v3);
+      }
+    }
+  }
+  // (2) weight gradient: thread j < 3*C*C owns dw[co][ci][k]; threads after that own dbias[co]
+  const int nvalid = min(kTB, a.T - t0);
+  if (threadIdx.x < 3 * C * C) {
+    const int co = threadIdx.x / (3 * C), r = threadIdx.x - co * 3 * C, ci = r / 3, k = r - ci * 3;
+    float acc = 0.f;
+    for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co] * s_a[(i + k) * C + ci];
+    atomicAdd(a.dw + threadIdx.x, acc);           // PyTorch layout [co][ci][k]
+  } else if (threadIdx.x < 3 * C * C + C) {
+    const int co = threadIdx.x - 3 * C * C;
+    float acc = 0.f;
+    for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co];
+    atomicAdd(a.dbias + co, acc);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    atomicAdd(a.dgamma + threadIdx.x, s_red[threadIdx.x]);
+    atomicAdd(a.dbeta + threadIdx.x, s_red[C + threadIdx.x]);
+  }
+  if (threadIdx.x < 2 * a.groups) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1, gsz = C / a.groups;
+    float tot = 0.f;
+    for (int c = g * gsz; c < (g + 1) * gsz; ++c) tot += s_red[(2 + which) * C + c];
+    atomicAdd(a.S + static_cast<size_t>(b) * 2 * a.groups + threadIdx.x, static_cast<double>(tot));
+  }
+}
+
+// ------------------------------------------------------------------------- stem_out_bwd
+constexpr int kSoMaxC0 = 64;
+constexpr int kSoMaxCo = 4;
+__global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_dyn[];
+  const int cin = a.cx + a.ca;
+  const int rows_h = kTB / a.f + 2;                 // low-res rows covering t0-1 .. t0+TB
+  float* s_w = s_dyn;                               // [co][3][c0]
+  float* s_h = s_w + a.co * 3 * a.c0;               // [rows_h][c0]
+  float* s_dy = s_h + rows_h * a.c0;                // [(TB+2)][co]  = dv * gate * gscale
+  float* s_dv = s_dy + (kTB + 2) * a.co;            // [TB][co]      = dv * gscale
+  float* s_xin = s_dv + kTB * a.co;                 // [TB][cin]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kTB;                  // multiple of f (TB % f == 0)
+  const int Tl = a.T / a.f;
+  const int q0 = t0 / a.f - 1;                      // first low-res row held in s_h
+  const int ldg = a.ld_gate > 0 ? a.ld_gate : a.co;
+  const float gscale = a.gscale ? a.gscale[0] : 1.f;
+  for (int i = threadIdx.x; i < a.co * 3 * a.c0; i += kTB) {
+    const int o = i / (3 * a.c0), r = i - o * 3 * a.c0, k = r / a.c0, c = r - k * a.c0;
+    s_w[i] = a.w[(o * a.c0 + c) * 3 + k];
+  }
+  const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(a.h) + static_cast<size_t>(b) * Tl * a.c0;
+  for (int i = threadIdx.x; i < rows_h * a.c0; i += kTB) {
+    const int r = i / a.c0, c = i - r * a.c0, q = q0 + r;
+    s_h[i] = (q >= 0 && q < Tl) ? __bfloat162float(hb[static_cast<size_t>(q) * a.c0 + c]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < (kTB + 2) * a.co; i += kTB) {
+    const int r = i / a.co, o = i - r * a.co, t = t0 - 1 + r;
+    float v = 0.f;
+    if (t >= 0 && t < a.T)
+      v = a.dv[(static_cast<size_t>(b) * a.co + o) * a.T + t] * gscale;
+    s_dy[i] = v * a.gate[static_cast<size_t>(b) * ldg + o];
+    if (r >= 1 && r <= kTB) s_dv[(r - 1) * a.co + o] = v;
+  }
+  float al = 1.f, be = 0.f;
+  if (a.noise) { al = a.alpha[b]; be = a.beta[b]; }
+  for (int i = threadIdx.x; i < kTB * cin; i += kTB) {
+    const int r = i / cin, c = i - r * cin, t = t0 + r;
+    float v = 0.f;
+    if (t < a.T) {
+      if (c < a.cx) {
+        const size_t idx = (static_cast<size_t>(b) * a.cx + c) * a.T + t;
+        v = a.x[idx];
+        if (a.noise) v = al * v + be * a.noise[idx];
+      } else {
+        v = a.append[(static_cast<size_t>(b) * a.ca + (c - a.cx)) * a.T + t];
+      }
+    }
+    s_xin[i] = v;
+  }
+  __syncthreads();
+  const int nvalid = min(kTB, a.T - t0);
+  // (1) dh: one thread per low-res row of the tile
+  const int nq = kTB / a.f;
+  if (threadIdx.x < nq) {
+    const int q = t0 / a.f + threadIdx.x;
+    if (q < Tl) {
+      __nv_bfloat16* dhp = static_cast<__nv_bfloat16*>(a.dh) + (static_cast<size_t>(b) * Tl + q) * a.c0;
+      for (int c8 = 0; c8 < a.c0; c8 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int u = q * a.f; u < q * a.f + a.f; ++u) {       // upsampled positions fed by row q
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int tp = u - k + 1;                          // output position using (u, k)
+            if (tp < 0 || tp >= a.T) continue;
+            const float* dyr = &s_dy[(tp - t0 + 1) * a.co];
+            for (int o = 0; o < a.co; ++o) {
+              const float g = dyr[o];
+              const float* wp = &s_w[(o * 3 + k) * a.c0 + c8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += g * wp[j];
+            }
+          }
+        }
+        *reinterpret_cast<uint4*>(dhp + c8) =
+            make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]),
+                       pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+      }
+    }
+  }
+  // (2) parameter gradients: flat work items, one dot product over the tile each
+  const int n_w = a.co * a.c0 * 3, n_ad = a.w_adapt ? a.co * cin : 0;
+  const int n_items = n_w + a.co /*bias*/ + a.co /*gate*/ + n_ad + (a.w_adapt ? a.co : 0);
+  for (int item = threadIdx.x; item < n_items; item += kTB) {
+    float acc = 0.f;
+    if (item < n_w) {                         // dw[co][c0][k] (PyTorch layout)
+      const int o = item / (a.c0 * 3), r = item - o * a.c0 * 3, c = r / 3, k = r - c * 3;
+      for (int i = 0; i < nvalid; ++i) {
+        const int u = t0 + i + k - 1;
+        if (u < 0 || u >= a.T) continue;
+        acc += s_dy[(i + 1) * a.co + o] * s_h[(u / a.f - q0) * a.c0 + c];
+      }
+      atomicAdd(a.dw + item, acc);
+    } else if (item < n_w + a.co) {           // dbias
+      const int o = item - n_w;
+      for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * a.co + o];
+      atomicAdd(a.dbias + o, acc);
+    } else if (item < n_w + 2 * a.co) {       // dgate[b][o] = sum dv * y,  y = conv(hup) + bias
+      const int o = item - n_w - a.co;
+      const float bo = a.bias ? a.bias[o] : 0.f;
+      for (int i = 0; i < nvalid; ++i) {
+        float y = bo;
+        for (int k = 0; k < 3; ++k) {
+          const int u = t0 + i + k - 1;
+          if (u < 0 || u >= a.T) continue;
+          const float* hr = &s_h[(u / a.f - q0) * a.c0];
+          const float* wp = &s_w[(o * 3 + k) * a.c0];
+          for (int c = 0; c < a.c0; ++c) y += hr[c] * wp[c];
+        }
+        acc += s_dv[i * a.co + o] * y;
+      }
+      atomicAdd(a.dgate + static_cast<size_t>(b) * a.ld_dgate + o, acc);
+    } else if (item < n_w + 2 * a.co + n_ad) {   // SkipAdapter weight [co][cin]
+      const int r = item - n_w - 2 * a.co, o = r / cin, c = r - o * cin;
+      for (int i = 0; i < nvalid; ++i) acc += s_dv[i * a.co + o] * s_xin[i * cin + c];
+      atomicAdd(a.dw_adapt + r, acc);
+    } else {                                      // SkipAdapter bias
+      const int o = item - n_w - 2 * a.co - n_ad;
+      for (int i = 0; i < nvalid; ++i) acc += s_dv[i * a.co + o];
+      atomicAdd(a.db_adapt + o, acc);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------- stem_in_bwd
+__global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float s_dyn[];
+  const int cin = a.cx + a.ca, ci_total = cin * a.f;
+  float* s_in = s_dyn;                      // [TB][ci_total]
+  float* s_g = s_in + kTB * ci_total;       // [TB][c0]
+  const int b = blockIdx.y;
+  const int To = a.T / a.f;
+  const int to0 = blockIdx.x * kTB;
+  float al = 1.f, be = 0.f;
+  if (a.noise) { al = a.alpha[b]; be = a.beta[b]; }
+  for (int i = threadIdx.x; i < kTB * ci_total; i += kTB) {
+    const int r = i / ci_total, ii = i - r * ci_total, c = ii / a.f, j = ii - c * a.f, to = to0 + r;
+    float v = 0.f;
+    if (to < To) {
+      const size_t tt = static_cast<size_t>(to) * a.f + j;
+      if (c < a.cx) {
+        const size_t idx = (static_cast<size_t>(b) * a.cx + c) * a.T + tt;
+        v = a.x[idx];
+        if (a.noise) v = al * v + be * a.noise[idx];
+      } else {
+        v = a.append[(static_cast<size_t>(b) * a.ca + (c - a.cx)) * a.T + tt];
+      }
+    }
+    s_in[i] = v;
+  }
+  const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(a.dout) + static_cast<size_t>(b) * To * a.c0;
+  for (int i = threadIdx.x; i < kTB * a.c0; i += kTB) {
+    const int r = i / a.c0, to = to0 + r;
+    s_g[i] = to < To ? __bfloat162float(gb[static_cast<size_t>(to) * a.c0 + (i - r * a.c0)]) : 0.f;
+  }
+  __syncthreads();
+  const int n_w = a.c0 * ci_total;
+  for (int item = threadIdx.x; item < n_w + a.c0; item += kTB) {
+    float acc = 0.f;
+    if (item < n_w) {                        // dw[c0][cin][f] flat == [c0][ci_total]
+      const int o = item / ci_total, ii = item - o * ci_total;
+      for (int i = 0; i < kTB; ++i) acc += s_g[i * a.c0 + o] * s_in[i * ci_total + ii];
+      atomicAdd(a.dw + item, acc);
+    } else {
+      const int o = item - n_w;
+      for (int i = 0; i < kTB; ++i) acc += s_g[i * a.c0 + o];
+      atomicAdd(a.dbias + o, acc);
+    }
+  }
+}
+
+}  // namespace adp
+
+using namespace adp;
+
+extern "C" int adp_narrow_conv_bwd(const adp_narrow_conv_bwd_args* args, adp_stream_t stream) {
+  ADP_CHECK(args && args->dy && args->x && args->stats_in && args->gamma && args->beta && args->w &&
+            args->dxh && args->dgamma && args->dbeta && args->S && args->dw && args->dbias,
+            "adp_narrow_conv_bwd: null pointer");
+  const adp_narrow_conv_bwd_args& a = *args;
+  ADP_CHECK(a.C == 8 && a.groups > 0 && a.C % a.groups == 0, "adp_narrow_conv_bwd: C=%d groups=%d", a.C, a.groups);
+  dim3 grid((a.T + kTB - 1) / kTB, a.B);
+  ADP_CUDA(launch_k(narrow_conv_bwd_kernel<8>, grid, dim3(kTB), (size_t)0, as_stream(stream), a));
+  return 0;
+}
+
+extern "C" int adp_stem_out_bwd(const adp_stem_out_bwd_args* args, adp_stream_t stream) {
+  ADP_CHECK(args && args->dv && args->h && args->x && args->w && args->gate && args->dh && args->dw &&
+            args->dbias && args->dgate, "adp_stem_out_bwd: null pointer");
+  const adp_stem_out_bwd_args& a = *args;
+  ADP_CHECK(a.co >= 1 && a.co <= kSoMaxCo && a.c0 % 8 == 0 && a.c0 <= kSoMaxC0 && a.cx + a.ca <= 8,
+            "adp_stem_out_bwd: co=%d c0=%d unsupported", a.co, a.c0);
+  ADP_CHECK(a.f >= 1 && kTB % a.f == 0 && a.T % a.f == 0, "adp_stem_out_bwd: f=%d", a.f);
+  ADP_CHECK(!a.w_adapt || (a.dw_adapt && a.db_adapt), "adp_stem_out_bwd: adapter grads missing");
+  ADP_CHECK((a.ca == 0) == (a.append == nullptr), "adp_stem_out_bwd: append / ca mismatch");
+  const int cin = a.cx + a.ca, rows_h = kTB / a.f + 2;
+  const size_t smem = (static_cast<size_t>(a.co) * 3 * a.c0 + static_cast<size_t>(rows_h) * a.c0 +
+                       static_cast<size_t>(kTB + 2) * a.co + static_cast<size_t>(kTB) * a.co +
+                       static_cast<size_t>(kTB) * cin) * sizeof(float);
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    ADP_CUDA(cudaFuncSetAttribute(stem_out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  dim3 grid((a.T + kTB - 1) / kTB, a.B);
+  ADP_CUDA(launch_k(stem_out_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
+  return 0;
+}
+
+extern "C" int adp_stem_in_bwd(const adp_stem_in_bwd_args* args, adp_stream_t stream) {
+  ADP_CHECK(args && args->dout && args->x && args->dw && args->dbias, "adp_stem_in_bwd: null pointer");
+  const adp_stem_in_bwd_args& a = *args;
+  ADP_CHECK((a.cx + a.ca) * a.f <= 32 && a.c0 % 8 == 0 && a.c0 <= 64 && a.T % a.f == 0,
+            "adp_stem_in_bwd: unsupported sizes");
+  ADP_CHECK((a.ca == 0) == (a.append == nullptr), "adp_stem_in_bwd: append / ca mismatch");
+  const size_t smem = (static_cast<size_t>(kTB) * (a.cx + a.ca) * a.f + static_cast<size_t>(kTB) * a.c0) * sizeof(float);
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    ADP_CUDA(cudaFuncSetAttribute(stem_in_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  dim3 grid((a.T / a.f + kTB - 1) / kTB, a.B);
+  ADP_CUDA(launch_k(stem_in_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
+  return 0;
+}

@@ -1,0 +1,208 @@
+// adp_wgrad: weight-gradient GEMM on tcgen05 (backward of adp_conv_gemm w.r.t. W).
+//
+//   dW[n = out channel][k = in channel] += sum_{b,t} G[b, t, g_col0 + n] * X[b, t + off, x_col0 + k]
+//
+// The reduction runs over TIME, which is the strided dimension of both channels-last
+// operands, so both are fed to the tensor core as MN-major tiles exactly as they lie in
+// memory (no transposes): a 64-time-step chunk of G is the A operand (M = 128 out channels =
+// two 64-channel swizzle chunks, LBO apart), the row-shifted chunk of X the B operand
+// (N = BN in channels).  TMA zero-fills rows outside [0,T) (conv padding) and channels beyond
+// the tensor (C < 64), so narrow levels just run padded tiles.  fp32 accumulation in TMEM
+// over the CTA's share of the (batch, time) chunks, then fp32 atomics into dW (split-K over
+// time across CTAs).  Warp roles: 0 TMA producer (+TMEM), 1 MMA issuer, 2-5 epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace adp {
+
+constexpr int kWgChunk = 64;          // time steps per pipeline stage
+constexpr int kWgBoxBytes = 64 * 128; // one TMA box: 64 rows x 64 channels bf16
+constexpr int kWgMaxStages = 8;
+
+struct WgradParams {
+  float* dw;
+  int ldw;                 // row pitch of dW in floats
+  int n_valid, k_valid;    // real out / in channel counts (tile masks)
+  int T, chunks_per_batch, total_chunks, chunks_per_split;
+  int g_col0, x_col0, off;
+  int n_stages, nb;        // nb = BN / 64 boxes of X per stage
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+             const WgradParams p) {
+  constexpr int NB = BN / 64;
+  constexpr int STAGE_BYTES = (2 + NB) * kWgBoxBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages];
+  __shared__ uint64_t acc_full;
+  __shared__ uint32_t tmem_slot;
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+  const int n0 = blockIdx.x * 128;             // out-channel tile
+  const int k0 = blockIdx.y * BN;              // in-channel tile
+  const int chunk_begin = blockIdx.z * p.chunks_per_split;
+  int chunk_end = chunk_begin + p.chunks_per_split;
+  if (chunk_end > p.total_chunks) chunk_end = p.total_chunks;
+
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmX);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = chunk_begin; c < chunk_end; ++c) {
+        const int b = c / p.chunks_per_batch;
+        const int t0 = (c - b * p.chunks_per_batch) * kWgChunk;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = ring + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_3d(st, &tmG, &full_bar[s], p.g_col0 + n0, t0, b);
+        tma_load_3d(st + kWgBoxBytes, &tmG, &full_bar[s], p.g_col0 + n0 + 64, t0, b);
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+          tma_load_3d(st + (2 + i) * kWgBoxBytes, &tmX, &full_bar[s], p.x_col0 + k0 + i * 64,
+                      t0 + p.off, b);
+        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
+      // MN-major SW128: 64-channel chunks kWgBoxBytes apart (LBO), 8-row groups 1024 B (SBO)
+      const uint64_t desc0 = umma_desc_mnmajor_sw128(smem_u32(ring), kWgBoxBytes);
+      int s = 0;
+      uint32_t ph = 0, accumulate = 0;
+      for (int c = chunk_begin; c < chunk_end; ++c) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t gdesc = desc0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
+        const uint64_t xdesc = gdesc + ((2 * kWgBoxBytes) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < kWgChunk / 16; ++kk) {      // 16 time steps per MMA = 2048 B
+          umma_bf16(tmem_base, gdesc + ((kk * 2048) >> 4), xdesc + ((kk * 2048) >> 4), idesc,
+                    accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(&acc_full);
+    }
+  } else {
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;           // this thread's out channel (TMEM lane)
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* drow = p.dw + static_cast<size_t>(n < p.n_valid ? n : 0) * p.ldw;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      tmem_ld_wait();
+      if (n < p.n_valid && chunk_end > chunk_begin) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = k0 + c0 + i;
+          if (k < p.k_valid) atomicAdd(drow + k, __uint_as_float(r[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+template <int BN>
+static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
+  constexpr int NB = BN / 64;
+  constexpr int STAGE_BYTES = (2 + NB) * kWgBoxBytes;
+  CUtensorMap tmG, tmX;
+  const uint32_t box[3] = {64, (uint32_t)kWgChunk, 1};
+  {
+    const uint64_t dims[3] = {(uint64_t)a.g_cols, (uint64_t)a.T, (uint64_t)a.B};
+    const uint64_t str[2] = {(uint64_t)a.ldg * 2, (uint64_t)a.T * a.ldg * 2};
+    if (int e = make_tmap_bf16(&tmG, a.g, 3, dims, str, box, 128)) return e;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.x_cols, (uint64_t)a.T, (uint64_t)a.B};
+    const uint64_t str[2] = {(uint64_t)a.ldx * 2, (uint64_t)a.T * a.ldx * 2};
+    if (int e = make_tmap_bf16(&tmX, a.x, 3, dims, str, box, 128)) return e;
+  }
+  WgradParams p;
+  p.dw = a.dw;
+  p.ldw = a.ldw;
+  p.n_valid = a.n;
+  p.k_valid = a.k;
+  p.T = a.T;
+  p.chunks_per_batch = (a.T + kWgChunk - 1) / kWgChunk;
+  p.total_chunks = a.B * p.chunks_per_batch;
+  p.g_col0 = a.g_col0;
+  p.x_col0 = a.x_col0;
+  p.off = a.off;
+  p.nb = NB;
+  int n_stages = (192 * 1024) / STAGE_BYTES;
+  if (n_stages > kWgMaxStages) n_stages = kWgMaxStages;
+  p.n_stages = n_stages;
+  const int n_tiles = (a.n + 127) / 128, k_tiles = (a.k + BN - 1) / BN;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int splits = (2 * sms) / (n_tiles * k_tiles);
+  if (splits < 1) splits = 1;
+  if (splits > p.total_chunks) splits = p.total_chunks;
+  p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
+  splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  const size_t smem = static_cast<size_t>(n_stages) * STAGE_BYTES + 1024;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    ADP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    smem_attr = smem;
+  }
+  dim3 grid(n_tiles, k_tiles, splits);
+  ADP_CUDA(launch_k(wgrad_kernel<BN>, grid, dim3(192), smem, stream, tmG, tmX, p));
+  return 0;
+}
+
+}  // namespace adp
+
+extern "C" int adp_wgrad(const adp_wgrad_args* args, adp_stream_t stream) {
+  using namespace adp;
+  ADP_CHECK(args && args->g && args->x && args->dw, "adp_wgrad: null pointer");
+  const adp_wgrad_args& a = *args;
+  ADP_CHECK(a.B > 0 && a.T > 0 && a.n > 0 && a.k > 0, "adp_wgrad: bad sizes");
+  ADP_CHECK(a.ldg % 8 == 0 && a.ldx % 8 == 0 && a.g_cols % 8 == 0 && a.x_cols % 8 == 0,
+            "adp_wgrad: pitches / extents must be multiples of 8");
+  ADP_CHECK(a.g_col0 % 8 == 0 && a.x_col0 % 8 == 0, "adp_wgrad: column offsets must be multiples of 8");
+  ADP_CHECK(a.g_col0 + a.n <= a.g_cols && a.x_col0 + a.k <= a.x_cols, "adp_wgrad: columns out of range");
+  cudaStream_t s = as_stream(stream);
+  if (a.k > 128) return launch_wgrad<256>(a, s);
+  if (a.k > 64) return launch_wgrad<128>(a, s);
+  return launch_wgrad<64>(a, s);
+}

@@ -14,7 +14,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import ConvGemmArgs, NarrowConvArgs, StemInArgs, StemOutArgs
+from ._lib import (ConvGemmArgs, NarrowConvArgs, NarrowConvBwdArgs, StemInArgs, StemInBwdArgs,
+                   StemOutArgs, StemOutBwdArgs, WgradArgs)
 
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 
@@ -293,3 +294,145 @@ def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:
                                                 x_next.data_ptr(), x.numel(), _stream()),
             "adp_sampler_step", lambda: ("sampler_step", 0, _nb(x, v, x_next)))
     return x_next
+
+
+# ----------------------------------------------------------------------------- backward
+def pack_conv_dgrad(w: Tensor) -> Tensor:
+    """Weights of the data-gradient conv: dA[t] = sum_j dOut[t + o_j] @ Wt_j with the taps
+    reversed and the matrices transposed ([co,ci,k] -> rows ci, K = (k reversed, co))."""
+    return pack_conv(w.flip(2).transpose(0, 1).contiguous())
+
+
+def wgrad(g: Tensor, x: Tensor, dw: Tensor, *, n: int, k: int, off: int = 0, g_col0: int = 0,
+          x_col0: int = 0) -> Tensor:
+    """dw[n_, k_] += sum_{b,t} g[b,t,g_col0+n_] * x[b,t+off,x_col0+k_]; g, x bf16 [B,T,ld]."""
+    a = WgradArgs()
+    a.g, a.x, a.dw = g.data_ptr(), x.data_ptr(), dw.data_ptr()
+    a.B, a.T = g.shape[0], g.shape[1]
+    a.n, a.k = n, k
+    a.ldg, a.ldx, a.ldw = g.stride(1), x.stride(1), dw.stride(0)
+    a.g_cols, a.x_cols = g.shape[2], x.shape[2]
+    a.g_col0, a.x_col0, a.off = g_col0, x_col0, off
+    _launch(lambda: _lib.lib().adp_wgrad(C.byref(a), _stream()), "adp_wgrad",
+            lambda: (f"wgrad[M={g.shape[0] * g.shape[1]} n={n} k={k}]",
+                     2.0 * g.shape[0] * g.shape[1] * n * k, (g.shape[0] * g.shape[1]) * (n + k) * 2))
+    return dw
+
+
+def gn_silu_bwd(da: Tensor, x: Tensor, stats: Tensor, gamma: Tensor, beta: Tensor, dxh: Tensor,
+                dgamma: Tensor, dbeta: Tensor, S: Tensor, groups: int, eps: float = 1e-5) -> Tensor:
+    B, T, Cc = x.shape
+    _launch(lambda: _lib.lib().adp_gn_silu_bwd(da.data_ptr(), x.data_ptr(), stats.data_ptr(),
+                                               gamma.data_ptr(), beta.data_ptr(), dxh.data_ptr(),
+                                               dgamma.data_ptr(), dbeta.data_ptr(), S.data_ptr(),
+                                               B, T, Cc, groups, eps, _stream()),
+            "adp_gn_silu_bwd", lambda: (f"gn_silu_bwd[M={B * T} C={Cc}]", 0, _nb(da, x, dxh)))
+    return dxh
+
+
+def gn_bwd_apply(dxh: Tensor, x: Tensor, stats: Tensor, S: Tensor, dx: Tensor, groups: int, *,
+                 dres: Optional[Tensor] = None, colsum: Optional[Tensor] = None,
+                 eps: float = 1e-5) -> Tensor:
+    B, T, Cc = x.shape
+    _launch(lambda: _lib.lib().adp_gn_bwd_apply(dxh.data_ptr(), x.data_ptr(), stats.data_ptr(),
+                                                S.data_ptr(), _p(dres), dx.data_ptr(), _p(colsum),
+                                                B, T, Cc, groups, eps, _stream()),
+            "adp_gn_bwd_apply", lambda: (f"gn_bwd_apply[M={B * T} C={Cc}]", 0, _nb(dxh, x, dres, dx)))
+    return dx
+
+
+def ln_film_bwd(dy: Tensor, x: Tensor, scale_shift: Optional[Tensor], ss_stride: int, dx: Tensor, *,
+                dss: Optional[Tensor] = None, dss_stride: int = 0,
+                colsum: Optional[Tensor] = None, eps: float = 1e-6) -> Tensor:
+    B, T, Cc = x.shape
+    _launch(lambda: _lib.lib().adp_ln_film_bwd(dy.data_ptr(), x.data_ptr(), _p(scale_shift),
+                                               ss_stride, dx.data_ptr(), _p(dss), dss_stride,
+                                               _p(colsum), B, T, Cc, eps, _stream()),
+            "adp_ln_film_bwd", lambda: (f"ln_film_bwd[M={B * T} C={Cc}]", 0, _nb(dy, x, dx)))
+    return dx
+
+
+def colsum(x: Tensor, out: Tensor, gate: Optional[Tensor] = None) -> Tensor:
+    B, T, Cc = x.shape
+    _launch(lambda: _lib.lib().adp_colsum(x.data_ptr(), _p(gate), 0 if gate is None else gate.stride(0),
+                                          out.data_ptr(), B, T, Cc, _stream()),
+            "adp_colsum", lambda: (f"colsum[M={B * T} C={Cc}]", 0, _nb(x)))
+    return out
+
+
+def skip_gate(y: Tensor, skip: Tensor, gate: Tensor, out: Tensor, stats: Optional[Tensor],
+              groups: int) -> Tensor:
+    B, T, Cc = y.shape
+    _launch(lambda: _lib.lib().adp_skip_gate(y.data_ptr(), skip.data_ptr(), gate.data_ptr(),
+                                             gate.stride(0), out.data_ptr(), _p(stats), B, T, Cc,
+                                             groups, _stream()),
+            "adp_skip_gate", lambda: (f"skip_gate[M={B * T} C={Cc}]", 0, _nb(y, skip, out)))
+    return out
+
+
+def skip_gate_bwd(dout: Tensor, y: Tensor, gate: Tensor, dys: Tensor, dgate: Tensor) -> Tensor:
+    B, T, Cc = y.shape
+    _launch(lambda: _lib.lib().adp_skip_gate_bwd(dout.data_ptr(), y.data_ptr(), gate.data_ptr(),
+                                                 gate.stride(0), dys.data_ptr(), dgate.data_ptr(),
+                                                 dgate.stride(0), B, T, Cc, _stream()),
+            "adp_skip_gate_bwd", lambda: (f"skip_gate_bwd[M={B * T} C={Cc}]", 0, _nb(dout, y, dys)))
+    return dys
+
+
+def cond_bwd(dss: Tensor, cond: Tensor, w: Tensor, dw: Tensor, dbias: Tensor, dcond: Tensor,
+             N: int) -> None:
+    B, K = cond.shape
+    _launch(lambda: _lib.lib().adp_cond_bwd(dss.data_ptr(), dss.stride(0), cond.data_ptr(),
+                                            w.data_ptr(), dw.data_ptr(), dbias.data_ptr(),
+                                            dcond.data_ptr(), B, N, K, _stream()),
+            "adp_cond_bwd", lambda: (f"cond_bwd[B={B} N={N} K={K}]", 4.0 * B * N * K, N * K * 6))
+
+
+def narrow_conv_bwd(dy: Tensor, x: Tensor, stats_in: Tensor, gamma: Tensor, beta: Tensor,
+                    w: Tensor, dxh: Tensor, dgamma: Tensor, dbeta: Tensor, S: Tensor, dw: Tensor,
+                    dbias: Tensor, groups: int, gn_eps: float = 1e-5) -> Tensor:
+    a = NarrowConvBwdArgs()
+    a.dy, a.x, a.stats_in = dy.data_ptr(), x.data_ptr(), stats_in.data_ptr()
+    a.gamma, a.beta, a.w = gamma.data_ptr(), beta.data_ptr(), w.data_ptr()
+    a.dxh, a.dgamma, a.dbeta, a.S = dxh.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), S.data_ptr()
+    a.dw, a.dbias = dw.data_ptr(), dbias.data_ptr()
+    a.B, a.T, a.C = x.shape
+    a.groups, a.gn_eps = groups, gn_eps
+    _launch(lambda: _lib.lib().adp_narrow_conv_bwd(C.byref(a), _stream()), "adp_narrow_conv_bwd",
+            lambda: (f"narrow_conv_bwd[M={x.shape[0] * x.shape[1]}]", 4.0 * x.numel() * 24, _nb(dy, x, dxh)))
+    return dxh
+
+
+def stem_out_bwd(dv: Tensor, h: Tensor, x: Tensor, w: Tensor, bias: Optional[Tensor], gate: Tensor,
+                 f: int, dh: Tensor, dw: Tensor, dbias: Tensor, dgate: Tensor, *,
+                 gscale: Optional[Tensor] = None, append: Optional[Tensor] = None,
+                 noise: Optional[Tensor] = None, alpha: Optional[Tensor] = None,
+                 beta: Optional[Tensor] = None, w_adapt: Optional[Tensor] = None,
+                 dw_adapt: Optional[Tensor] = None, db_adapt: Optional[Tensor] = None) -> Tensor:
+    a = StemOutBwdArgs()
+    a.dv, a.gscale, a.h, a.x, a.append = dv.data_ptr(), _p(gscale), h.data_ptr(), x.data_ptr(), _p(append)
+    a.noise, a.alpha, a.beta = _p(noise), _p(alpha), _p(beta)
+    a.w, a.bias, a.w_adapt, a.gate = w.data_ptr(), _p(bias), _p(w_adapt), gate.data_ptr()
+    a.dh, a.dw, a.dbias, a.dgate = dh.data_ptr(), dw.data_ptr(), dbias.data_ptr(), dgate.data_ptr()
+    a.dw_adapt, a.db_adapt = _p(dw_adapt), _p(db_adapt)
+    a.B, a.cx, a.T = x.shape
+    a.ca = 0 if append is None else append.shape[1]
+    a.c0, a.co, a.f = h.shape[-1], w.shape[0], f
+    a.ld_gate, a.ld_dgate = gate.stride(0), dgate.stride(0)
+    _launch(lambda: _lib.lib().adp_stem_out_bwd(C.byref(a), _stream()), "adp_stem_out_bwd",
+            lambda: ("stem_out_bwd", 0, _nb(dv, h, x, dh)))
+    return dh
+
+
+def stem_in_bwd(dout: Tensor, x: Tensor, dw: Tensor, dbias: Tensor, f: int, *,
+                append: Optional[Tensor] = None, noise: Optional[Tensor] = None,
+                alpha: Optional[Tensor] = None, beta: Optional[Tensor] = None) -> None:
+    a = StemInBwdArgs()
+    a.dout, a.x, a.append = dout.data_ptr(), x.data_ptr(), _p(append)
+    a.noise, a.alpha, a.beta = _p(noise), _p(alpha), _p(beta)
+    a.dw, a.dbias = dw.data_ptr(), dbias.data_ptr()
+    a.B, a.cx, a.T = x.shape
+    a.ca = 0 if append is None else append.shape[1]
+    a.c0, a.f = dout.shape[-1], f
+    _launch(lambda: _lib.lib().adp_stem_in_bwd(C.byref(a), _stream()), "adp_stem_in_bwd",
+            lambda: ("stem_in_bwd", 0, _nb(dout, x)))

@@ -259,6 +259,17 @@ class B200UNet(nn.Module):
         v = self._version()
         if self._packed is not None and self._packed_version == v:
             return self._packed
+        if self._packed is not None:
+            # weights changed (optimizer step): refresh the SAME tensors in place, so captured
+            # CUDA graphs and plans that hold their addresses stay valid
+            _copy_tree(self._packed, self._compute_packed())
+            self._packed_version = v
+            return self._packed
+        self._packed, self._packed_version = self._compute_packed(), v
+        return self._packed
+
+    @torch.no_grad()
+    def _compute_packed(self):
         P: Dict = {}
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         cond_w, cond_b, off = [], [], 0
@@ -340,7 +351,6 @@ class B200UNet(nn.Module):
             P["time"] = {"freqs": f32(t.weights), "w_emb": w_emb.contiguous(), "b_emb": f32(t.to_out.bias),
                          "w_mlp": t.mlp.weight.detach().to(torch.bfloat16).contiguous(),
                          "b_mlp": f32(t.mlp.bias), "kpad": kpad}
-        self._packed, self._packed_version = P, v
         return P
 
     # --------------------------------------------------------------------- plan
@@ -563,11 +573,11 @@ class B200UNet(nn.Module):
 
     def _plan(self, B: int, T: int, Bh: int, M: int, mode: str, baked: Tuple = ()) -> _Plan:
         """`baked` = host-side values frozen into the captured graph (cfg scale, features flag)."""
-        key = (B, T, Bh, M, mode, baked, self._version())
+        key = (B, T, Bh, M, mode, baked)
+        self.packed()                      # refreshes the packed weights in place if needed
         plan = self._plans.get(key)
         if plan is None:
             ops.device_check()
-            self._plans = {k: v for k, v in self._plans.items() if k[-1] == key[-1]}
             plan = self._plans[key] = self._build_plan(B, T, Bh, M, mode)
         return plan
 
@@ -685,6 +695,18 @@ class B200UNet(nn.Module):
             plan.sigma.copy_(sig[i], non_blocking=True)
             self._execute(plan)
         return plan.x.clone().to(x_noisy.dtype)
+
+
+def _copy_tree(dst, src) -> None:
+    """In-place refresh of a nested dict/list/tuple of tensors (same structure)."""
+    if isinstance(dst, Tensor):
+        dst.copy_(src)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_tree(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for d, s_ in zip(dst, src):
+            _copy_tree(d, s_)
 
 
 def _pad_to(t: Tensor, n: int) -> Tensor:

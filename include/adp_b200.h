@@ -200,6 +200,113 @@ int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t stream);
 int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_next, int64_t n,
                      adp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Backward (training) entry points: VDiffusion loss.backward() through UNetV0
+ * (reference diffusion.py:82-95 + autograd over the a_unet blocks).  Data gradients are
+ * channels-last bf16; parameter gradients accumulate in fp32 buffers zeroed by the caller.
+ * The data gradient of every conv / linear is adp_conv_gemm with transposed packed weights.
+ */
+
+/* dW[n][k] += sum_{b,t} g[b][t][g_col0+n] * x[b][t+off][x_col0+k]  (tcgen05, both operands
+ * consumed MN-major in place; rows outside [0,T) read as zero).  Backward of adp_conv_gemm
+ * w.r.t. one tap of W. */
+typedef struct adp_wgrad_args {
+  const void* g;      /* bf16 [B][T][ldg] output gradient                 */
+  const void* x;      /* bf16 [B][T][ldx] forward input of the GEMM       */
+  float* dw;          /* fp32 [n][ldw]                                    */
+  int32_t B, T;
+  int32_t n, k;       /* out / in channels of this tap                    */
+  int32_t ldg, ldx, ldw;
+  int32_t g_cols, x_cols; /* valid columns of g / x rows (TMA extents)    */
+  int32_t g_col0, x_col0, off;
+} adp_wgrad_args;
+int adp_wgrad(const adp_wgrad_args* args, adp_stream_t stream);
+
+/* GroupNorm+SiLU backward, pass 1: dxh = da*silu'(z)*gamma; dgamma += sum dz*xhat;
+ * dbeta += sum dz; S[b][g] += (sum dxh, sum dxh*xhat). */
+int adp_gn_silu_bwd(const void* da, const void* x, const double* stats, const float* gamma,
+                    const float* beta, void* dxh, float* dgamma, float* dbeta, double* S,
+                    int32_t B, int32_t T, int32_t C, int32_t groups, float eps,
+                    adp_stream_t stream);
+/* pass 2: dx = rstd*(dxh - S1/n - xhat*S2/n) [+ dres]; optional colsum[c] += sum dx. */
+int adp_gn_bwd_apply(const void* dxh, const void* x, const double* stats, const double* S,
+                     const void* dres, void* dx, float* colsum, int32_t B, int32_t T, int32_t C,
+                     int32_t groups, float eps, adp_stream_t stream);
+/* Modulation backward: dx, dss[b][0:C] += sum_t dy*xhat, dss[b][C:2C] += sum_t dy. */
+int adp_ln_film_bwd(const void* dy, const void* x, const float* scale_shift, int32_t ss_stride,
+                    void* dx, float* dss, int32_t dss_stride, float* colsum, int32_t B, int32_t T,
+                    int32_t C, float eps, adp_stream_t stream);
+/* out[c] += sum_{b,t} x[b][t][c] * (gate ? gate[b][c] : 1)   (bias gradients) */
+int adp_colsum(const void* x, const float* gate, int32_t ld_gate, float* out, int32_t B, int32_t T,
+               int32_t C, adp_stream_t stream);
+/* MergeModulate as its own pass (training forward keeps the pre-gate conv output y):
+ * out = skip + gate[b][c]*y (+ GroupNorm statistics of out). */
+int adp_skip_gate(const void* y, const void* skip, const float* gate, int32_t ld_gate, void* out,
+                  double* stats, int32_t B, int32_t T, int32_t C, int32_t groups,
+                  adp_stream_t stream);
+/* dys = gate*dout; dgate[b][c] += sum_t dout*y. */
+int adp_skip_gate_bwd(const void* dout, const void* y, const float* gate, int32_t ld_gate,
+                      void* dys, float* dgate, int32_t ld_dgate, int32_t B, int32_t T, int32_t C,
+                      adp_stream_t stream);
+/* Backward of the concatenated conditioning projection ss = cond W^T + b:
+ * dw[n][k] = sum_b dss[b][n]*cond[b][k]; dbias[n] = sum_b dss[b][n]; dcond += dss W. */
+int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond, const void* w, float* dw,
+                 float* dbias, float* dcond, int32_t B, int32_t N, int32_t K, adp_stream_t stream);
+
+typedef struct adp_narrow_conv_bwd_args {
+  const void* dy;           /* bf16 [B][T][C] gradient of the conv output        */
+  const void* x;            /* bf16 [B][T][C] ConvBlock input (pre GroupNorm)     */
+  const double* stats_in;   /* fp64 [B][groups][2] of x                           */
+  const float* gamma;
+  const float* beta;
+  const float* w;           /* fp32 [C][C][3]                                     */
+  void* dxh;                /* bf16 [B][T][C] -> adp_gn_bwd_apply                 */
+  float* dgamma;
+  float* dbeta;
+  double* S;                /* fp64 [B][groups][2]                                */
+  float* dw;                /* fp32 [C][C][3]                                     */
+  float* dbias;             /* fp32 [C]                                           */
+  int32_t B, T, C, groups;
+  float gn_eps;
+} adp_narrow_conv_bwd_args;
+int adp_narrow_conv_bwd(const adp_narrow_conv_bwd_args* args, adp_stream_t stream);
+
+typedef struct adp_stem_out_bwd_args {
+  const float* dv;          /* fp32 [B][co][T]  dL/dv (adp_stem_out's `dv`)       */
+  const float* gscale;      /* fp32 [1] upstream gradient of the loss, or NULL    */
+  const void* h;            /* bf16 [B][T/f][c0]                                  */
+  const float* x;           /* fp32 [B][cx][T]                                    */
+  const float* append;
+  const float* noise;
+  const float* alpha;
+  const float* beta;
+  const float* w;           /* fp32 [co][c0][3]                                   */
+  const float* bias;
+  const float* w_adapt;     /* non-NULL iff the skip adapter exists               */
+  const float* gate;        /* fp32 [B][ld_gate]                                  */
+  void* dh;                 /* bf16 [B][T/f][c0]                                  */
+  float* dw;
+  float* dbias;
+  float* dgate;             /* fp32 [B][ld_dgate]                                 */
+  float* dw_adapt;
+  float* db_adapt;
+  int32_t B, T, cx, ca, c0, co, f, ld_gate, ld_dgate;
+} adp_stem_out_bwd_args;
+int adp_stem_out_bwd(const adp_stem_out_bwd_args* args, adp_stream_t stream);
+
+typedef struct adp_stem_in_bwd_args {
+  const void* dout;         /* bf16 [B][T/f][c0]                                  */
+  const float* x;
+  const float* append;
+  const float* noise;
+  const float* alpha;
+  const float* beta;
+  float* dw;                /* fp32 [c0][cx+ca][f]                                */
+  float* dbias;             /* fp32 [c0]                                          */
+  int32_t B, T, cx, ca, c0, f;
+} adp_stem_in_bwd_args;
+int adp_stem_in_bwd(const adp_stem_in_bwd_args* args, adp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

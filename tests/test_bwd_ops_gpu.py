@@ -1,0 +1,223 @@
+"""Backward kernels against torch.autograd of the fp32 PyTorch restatement of each op
+(same bf16-rounded inputs).  Gradient outputs that are bf16 get 2^-6 relative + small
+absolute slack; fp32 parameter-gradient accumulators (sums over up to 10^5 terms of bf16
+products) get 1e-2 relative to the largest entry."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def close(got, ref, rtol, atol_frac, what):
+    got, ref = got.double(), ref.double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{what}: max abs err {err:.4e} (ref max {scale:.3e})")
+    assert err <= rtol * scale + atol_frac * scale + 1e-12, f"{what}: {err} vs scale {scale}"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audio_diffusion_pytorch_b200 import ops
+    ops.device_check()
+    return ops
+
+
+def stats_of(y, groups):
+    B, T, Cc = y.shape
+    yg = y.double().reshape(B, T, groups, Cc // groups)
+    return torch.stack([yg.sum(dim=(1, 3)), (yg * yg).sum(dim=(1, 3))], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize("B,T,n,k,off", [(2, 256, 64, 64, 0), (2, 300, 128, 128, -1), (1, 128, 32, 32, 1),
+                                         (2, 1000, 256, 256, 0), (1, 64, 1024, 512, 1),
+                                         (3, 100, 8, 32, 0), (2, 4096, 64, 64, -1)])
+def test_wgrad(ops, B, T, n, k, off):
+    g = bf(rnd(B, T, n, seed=1))
+    x = bf(rnd(B, T, k, seed=2))
+    dw = torch.zeros(n, k, device=DEV)
+    ops.wgrad(g, x, dw, n=n, k=k, off=off)
+    xs = torch.zeros_like(x.float())
+    if off == 0:
+        xs = x.float()
+    elif off > 0:
+        xs[:, :-off] = x.float()[:, off:]
+    else:
+        xs[:, -off:] = x.float()[:, :off]
+    ref = torch.einsum("btn,btk->nk", g.float(), xs)
+    close(dw, ref, 2e-3, 1e-3, f"wgrad n{n} k{k} off{off}")
+
+
+def test_wgrad_column_views(ops):
+    """Phase views of the upsample conv: g is a column block of a wider row."""
+    B, T, co, ci, f = 2, 256, 64, 128, 2
+    g = bf(rnd(B, T, f * co, seed=3))
+    x = bf(rnd(B, T, ci, seed=4))
+    dw = torch.zeros(co, ci, device=DEV)
+    ops.wgrad(g, x, dw, n=co, k=ci, off=0, g_col0=co)
+    ref = torch.einsum("btn,btk->nk", g.float()[..., co:], x.float())
+    close(dw, ref, 2e-3, 1e-3, "wgrad column view")
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 1000, 8), (2, 512, 32), (2, 300, 64), (1, 256, 512), (2, 128, 1024)])
+def test_gn_silu_backward(ops, B, T, C):
+    groups = 8
+    x = bf(rnd(B, T, C, seed=5) * 1.5 + 0.3)
+    da = bf(rnd(B, T, C, seed=6))
+    dres = bf(rnd(B, T, C, seed=7))
+    gamma = (rnd(C, seed=8) * 0.2 + 1.0).requires_grad_()
+    beta = (rnd(C, seed=9) * 0.2).requires_grad_()
+    xr = x.float().requires_grad_()
+    a = F.silu(F.group_norm(xr.transpose(1, 2), groups, gamma, beta, 1e-5)).transpose(1, 2)
+    a.backward(da.float())
+    stats = stats_of(x, groups)
+    dxh, dx = torch.empty_like(x), torch.empty_like(x)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    S = torch.zeros(B, groups, 2, dtype=torch.float64, device=DEV)
+    cs = torch.zeros(C, device=DEV)
+    ops.gn_silu_bwd(da, x, stats, gamma.detach(), beta.detach(), dxh, dg, db, S, groups)
+    ops.gn_bwd_apply(dxh, x, stats, S, dx, groups, dres=dres, colsum=cs)
+    close(dx, xr.grad + dres.float(), 2 ** -6, 2e-3, f"gn bwd dx C{C}")
+    close(dg, gamma.grad, 1e-2, 2e-3, f"gn bwd dgamma C{C}")
+    close(db, beta.grad, 1e-2, 2e-3, f"gn bwd dbeta C{C}")
+    close(cs, dx.float().sum(dim=(0, 1)), 1e-3, 1e-3, "gn bwd colsum")
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 1000, 8), (2, 512, 32), (2, 300, 64), (1, 256, 512), (2, 128, 1024)])
+def test_ln_film_backward(ops, B, T, C):
+    x = bf(rnd(B, T, C, seed=10) * 2.0 + 0.5)
+    dy = bf(rnd(B, T, C, seed=11))
+    ss = (rnd(B, 2 * C, seed=12) * 0.3).requires_grad_()
+    xr = x.float().requires_grad_()
+    y = F.layer_norm(xr, (C,), eps=1e-6) * (1 + ss[:, None, :C]) + ss[:, None, C:]
+    y.backward(dy.float())
+    dx = torch.empty_like(x)
+    dss = torch.zeros(B, 2 * C, device=DEV)
+    cs = torch.zeros(C, device=DEV)
+    ops.ln_film_bwd(dy, x, ss.detach(), 2 * C, dx, dss=dss, dss_stride=2 * C, colsum=cs)
+    close(dx, xr.grad, 2 ** -6, 2e-3, f"ln_film bwd dx C{C}")
+    close(dss, ss.grad, 1e-2, 2e-3, f"ln_film bwd dss C{C}")
+    close(cs, dx.float().sum(dim=(0, 1)), 1e-3, 1e-3, "ln_film bwd colsum")
+
+
+def test_colsum_and_skip_gate(ops):
+    B, T, C, groups = 2, 700, 64, 8
+    y, skip, dout = bf(rnd(B, T, C, seed=13)), bf(rnd(B, T, C, seed=14)), bf(rnd(B, T, C, seed=15))
+    gate = rnd(B, 72, seed=16)[:, :C]          # strided view, like a slice of ss_all
+    out = torch.empty_like(y)
+    stats = torch.zeros(B, groups, 2, dtype=torch.float64, device=DEV)
+    ops.skip_gate(y, skip, gate, out, stats, groups)
+    ref = skip.float() + gate[:, None, :] * y.float()
+    close(out, ref, 2 ** -7, 1e-3, "skip_gate out")
+    close(stats, stats_of(out, groups), 1e-4, 1e-6, "skip_gate stats")
+    dys = torch.empty_like(y)
+    dgate = torch.zeros(B, 72, device=DEV)
+    ops.skip_gate_bwd(dout, y, gate, dys, dgate[:, :C])
+    close(dys, gate[:, None, :] * dout.float(), 2 ** -7, 1e-3, "skip_gate_bwd dys")
+    close(dgate[:, :C], (dout.float() * y.float()).sum(1), 1e-3, 1e-3, "skip_gate_bwd dgate")
+    cs = torch.zeros(C, device=DEV)
+    ops.colsum(dout, cs, gate)
+    close(cs, (dout.float() * gate[:, None, :]).sum(dim=(0, 1)), 1e-3, 1e-3, "colsum gated")
+
+
+def test_cond_bwd(ops):
+    B, N, K = 4, 840, 1024
+    dss = rnd(B, N + 8, seed=17)[:, :N]
+    cond = bf(rnd(B, K, seed=18)).float()
+    w = bf(rnd(N, K, seed=19) * 0.03)
+    dw, dbias, dcond = torch.empty(N, K, device=DEV), torch.empty(N, device=DEV), torch.zeros(B, K, device=DEV)
+    ops.cond_bwd(dss, cond, w, dw, dbias, dcond, N)
+    close(dw, dss.t() @ cond, 1e-4, 1e-5, "cond_bwd dw")
+    close(dbias, dss.sum(0), 1e-4, 1e-5, "cond_bwd dbias")
+    close(dcond, dss @ w.float(), 1e-3, 1e-4, "cond_bwd dcond")
+
+
+def test_narrow_conv_backward(ops):
+    B, T, C, groups = 2, 3000, 8, 8
+    x = bf(rnd(B, T, C, seed=20) * 1.3 + 0.2)
+    dy = bf(rnd(B, T, C, seed=21))
+    gamma = (rnd(C, seed=22) * 0.2 + 1.0).requires_grad_()
+    beta = (rnd(C, seed=23) * 0.2).requires_grad_()
+    w = rnd(C, C, 3, scale=(3 * C) ** -0.5, seed=24).requires_grad_()
+    bias = rnd(C, seed=25).requires_grad_()
+    xr = x.float().requires_grad_()
+    a = F.silu(F.group_norm(xr.transpose(1, 2), groups, gamma, beta, 1e-5))
+    y = F.conv1d(a, w, bias, padding=1).transpose(1, 2)
+    y.backward(dy.float())
+    stats = stats_of(x, groups)
+    dxh, dx = torch.empty_like(x), torch.empty_like(x)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dw, dbias = torch.zeros(C, C, 3, device=DEV), torch.zeros(C, device=DEV)
+    S = torch.zeros(B, groups, 2, dtype=torch.float64, device=DEV)
+    ops.narrow_conv_bwd(dy, x, stats, gamma.detach(), beta.detach(), w.detach(), dxh, dg, db, S, dw,
+                        dbias, groups)
+    ops.gn_bwd_apply(dxh, x, stats, S, dx, groups)
+    close(dx, xr.grad, 2 ** -6, 3e-3, "narrow bwd dx")
+    close(dw, w.grad, 1e-2, 2e-3, "narrow bwd dw")
+    close(dbias, bias.grad, 1e-3, 1e-3, "narrow bwd dbias")
+    close(dg, gamma.grad, 1e-2, 2e-3, "narrow bwd dgamma")
+    close(db, beta.grad, 1e-2, 2e-3, "narrow bwd dbeta")
+
+
+@pytest.mark.parametrize("cx,ca,co,c0,f", [(2, 0, 2, 8, 1), (2, 2, 2, 8, 1), (1, 1, 1, 32, 4)])
+def test_stem_backward(ops, cx, ca, co, c0, f):
+    B, T = 2, 1024
+    cin = cx + ca
+    h = bf(rnd(B, T // f, c0, seed=26))
+    x = rnd(B, cx, T, seed=27)
+    app = rnd(B, ca, T, seed=28) if ca else None
+    noise = rnd(B, cx, T, seed=29)
+    alpha, beta = torch.rand(B, device=DEV), torch.rand(B, device=DEV)
+    w = rnd(co, c0, 3, scale=(3 * c0) ** -0.5, seed=30).requires_grad_()
+    bias = rnd(co, seed=31).requires_grad_()
+    gate = rnd(B, co, seed=32).requires_grad_()
+    adapt = cin != co
+    wa = rnd(co, cin, seed=33).requires_grad_() if adapt else None
+    ba = rnd(co, seed=34).requires_grad_() if adapt else None
+    dv = rnd(B, co, T, seed=35)
+    hr = h.float().requires_grad_()
+    xin = alpha[:, None, None] * x + beta[:, None, None] * noise
+    xin_full = torch.cat([xin, app], 1) if ca else xin
+    up = F.interpolate(hr.transpose(1, 2), scale_factor=f, mode="nearest")
+    y = F.conv1d(up, w, bias, padding=1)
+    skip = F.conv1d(xin_full, wa[:, :, None], ba) if adapt else xin_full
+    v = skip + gate[:, :, None] * y
+    v.backward(dv)
+    dh = torch.empty_like(h)
+    dw, db = torch.zeros(co, c0, 3, device=DEV), torch.zeros(co, device=DEV)
+    dgate = torch.zeros(B, co, device=DEV)
+    dwa = torch.zeros(co, cin, device=DEV) if adapt else None
+    dba = torch.zeros(co, device=DEV) if adapt else None
+    ops.stem_out_bwd(dv, h, x, w.detach(), bias.detach(), gate.detach(), f, dh, dw, db, dgate,
+                     append=app, noise=noise, alpha=alpha, beta=beta,
+                     w_adapt=wa.detach() if adapt else None, dw_adapt=dwa, db_adapt=dba)
+    close(dh, hr.grad, 2 ** -6, 2e-3, "stem_out_bwd dh")
+    close(dw, w.grad, 1e-3, 1e-3, "stem_out_bwd dw")
+    close(db, bias.grad, 1e-3, 1e-3, "stem_out_bwd dbias")
+    close(dgate, gate.grad, 1e-3, 1e-3, "stem_out_bwd dgate")
+    if adapt:
+        close(dwa, wa.grad, 1e-3, 1e-3, "stem_out_bwd dw_adapt")
+        close(dba, ba.grad, 1e-3, 1e-3, "stem_out_bwd db_adapt")
+    # stem_in backward
+    w_in = rnd(c0, cin, f, seed=36).requires_grad_()
+    b_in = rnd(c0, seed=37).requires_grad_()
+    dout = bf(rnd(B, T // f, c0, seed=38))
+    out = F.conv1d(xin_full, w_in, b_in, stride=f).transpose(1, 2)
+    out.backward(dout.float())
+    dwi, dbi = torch.zeros(c0, cin, f, device=DEV), torch.zeros(c0, device=DEV)
+    ops.stem_in_bwd(dout, x, dwi, dbi, f, append=app, noise=noise, alpha=alpha, beta=beta)
+    close(dwi, w_in.grad, 1e-3, 1e-3, "stem_in_bwd dw")
+    close(dbi, b_in.grad, 1e-3, 1e-3, "stem_in_bwd dbias")
