@@ -143,6 +143,52 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+UPSAMPLER = dict(upsample_factor=16, in_channels=2,
+                 channels=[8, 32, 64, 128, 256, 512, 512, 1024, 1024],
+                 factors=[1, 4, 4, 4, 2, 2, 2, 2, 2], items=[1, 2, 2, 2, 2, 2, 2, 4, 4])
+
+
+def train_step_bench(adp, dev, world, dist, steps, warmup, batch=4):
+    """BASELINE configs[3]: DiffusionUpsampler(upsample_factor=16) training step -- fused loss,
+    hand-written backward, gradient all-reduce over NCCL (DDP) when world > 1, fused AdamW --
+    `batch` clips of [2, 2**18] per GPU.  Returns ms per step (device-timed, max over ranks)."""
+    model = adp.DiffusionUpsampler(net_t=adp.UNetV0, **UPSAMPLER).to(dev)
+    step_model = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        step_model = DDP(model, device_ids=[dev.index], bucket_cap_mb=100, gradient_as_bucket_view=True)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    audio = torch.randn(batch, 2, LENGTH, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = step_model(audio)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return {"ms_per_step": float(ms.item()), "loss": float(loss), "batch_per_gpu": batch,
+            "config": "configs[3]: DiffusionUpsampler upsample_factor=16, [B,2,2**18], fwd+bwd+"
+                      "AdamW" + ("+NCCL grad all-reduce (DDP)" if world > 1 else ""),
+            "audio_s_per_s": batch * world * CLIP_SECONDS / (float(ms.item()) * 1e-3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,6 +197,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-kernel table")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,6 +303,10 @@ def main():
             "gpu_launches": plan.n_kernels * NUM_STEPS * args.steps,
             "ms_per_net_eval": ms_per_step / NUM_STEPS,
             "roofline": roof}
+    if not args.no_train:
+        del model, net, plan
+        torch.cuda.empty_cache()
+        line["train_step"] = train_step_bench(adp, dev, world, dist, steps=5, warmup=3)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         v, per_step, cores, sample = cpu_reference_run(steps=1, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",

@@ -22,7 +22,7 @@ def compare_grads(ref_params, got_params):
     worst, dots, n1, n2 = 0.0, 0.0, 0.0, 0.0
     # gradients that are analytically zero (a conv bias feeding a GroupNorm with one channel per
     # group) are compared on the scale of a typical parameter gradient, not on their own
-    floor = 1e-3 * float(torch.stack([p.grad.double().norm() for _, p in ref_params]).median())
+    floor = 0.1 * float(torch.stack([p.grad.double().norm() for _, p in ref_params]).median())
     for (name, p), q in zip(ref_params, got_params):
         assert q.grad is not None, f"no gradient for {name}"
         g_ref, g = p.grad.double(), q.grad.double().cpu()
