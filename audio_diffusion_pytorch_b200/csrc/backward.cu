@@ -169,7 +169,7 @@ gn_bwd_apply_kernel(const uint4* __restrict__ dxh, const uint4* __restrict__ x,
       float orr[8];
       unpack8(ov, orr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acs[j] += orr[j];
+      for (int j = 0; j < 8; ++j) acs[j] += o[j];   // bias gradients sum the unrounded fp32 values
     }
   }
   if (colsum) {
@@ -269,7 +269,7 @@ ln_film_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
           float orr[8];
           unpack8(ov, orr);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acs[it][j] += orr[j];
+          for (int j = 0; j < 8; ++j) acs[it][j] += o[j];
         }
       }
     }
@@ -480,7 +480,7 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
 }
 
 static int grid_for(size_t nvec, int B) {
-  size_t g = (nvec + 256 * 8 - 1) / (256 * 8);
+  size_t g = (nvec + 256 * 2 - 1) / (256 * 2);
   const size_t cap = 148 * 8 / (B < 8 ? B : 8) + 1;
   if (g > cap) g = cap;
   if (g < 1) g = 1;

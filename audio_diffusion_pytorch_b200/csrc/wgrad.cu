@@ -122,10 +122,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       tmem_ld32(taddr + c0, r);
       tmem_ld_wait();
       if (n < p.n_valid && chunk_end > chunk_begin) {
+        if (gridDim.z == 1 && k0 + c0 + 32 <= p.k_valid && (p.ldw & 3) == 0) {
+          // single writer of this tile (dW is pre-zeroed): plain 16-byte stores
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = k0 + c0 + i;
-          if (k < p.k_valid) atomicAdd(drow + k, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(drow + k0 + c0 + i) =
+                make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                            __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int k = k0 + c0 + i;
+            if (k < p.k_valid) atomicAdd(drow + k, __uint_as_float(r[i]));
+          }
         }
       }
     }
@@ -173,9 +182,10 @@ static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // split-K over time: every split ends in 128 x BN fp32 atomics, so keep >= 16 chunks per CTA
   int splits = (2 * sms) / (n_tiles * k_tiles);
+  if (splits > p.total_chunks / 16) splits = p.total_chunks / 16;
   if (splits < 1) splits = 1;
-  if (splits > p.total_chunks) splits = p.total_chunks;
   p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
   splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   const size_t smem = static_cast<size_t>(n_stages) * STAGE_BYTES + 1024;

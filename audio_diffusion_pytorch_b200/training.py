@@ -135,6 +135,7 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
             dr, dh, dx, dxh = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
             if narrow:
                 dw1, dw2 = grad_for(r_.conv1.weight), grad_for(r_.conv2.weight)
+                db_scratch = gbuf((C,))
                 plan.fwd.append(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.narrow_conv(
                     x, h, s, ip["gn1"][0], ip["gn1"][1], ip["w1"], ip["b1"], G, stats_out=hs))
                 plan.fwd.append(lambda x=x, h=h, rr=rr, hs=h_stats, ip=ip: ops.narrow_conv(
@@ -144,14 +145,14 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
 
                 def bwd(dy, x=x, h=h, rr=rr, ss=ss, dss=dss, xs=x_stats, hs=h_stats, ip=ip, dr=dr,
                         dh=dh, dx=dx, dxh=dxh, S1=S1, S2=S2, dgn1=dgn1, dgn2=dgn2, dw1=dw1, dw2=dw2,
-                        db1=db1, db2=db2):
+                        db1=db1, db2=db2, db_scratch=db_scratch):
                     ops.ln_film_bwd(dy, rr, ss, ss_stride, dr, dss=dss, dss_stride=ss_stride,
                                     eps=net.MOD_LN_EPS)
                     ops.narrow_conv_bwd(dr, h, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], dxh, dgn2[0],
                                         dgn2[1], S2, dw2, db2, G)
-                    ops.gn_bwd_apply(dxh, h, hs, S2, dh, G)
+                    ops.gn_bwd_apply(dxh, h, hs, S2, dh, G, colsum=db1)   # fp32 sum, pre-rounding
                     ops.narrow_conv_bwd(dh, x, xs, ip["gn1"][0], ip["gn1"][1], ip["w1"], dxh, dgn1[0],
-                                        dgn1[1], S1, dw1, db1, G)
+                                        dgn1[1], S1, dw1, db_scratch, G)
                     ops.gn_bwd_apply(dxh, x, xs, S1, dx, G, dres=dr)
                     return dx
             else:
