@@ -211,6 +211,7 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
