@@ -50,6 +50,12 @@ struct Gemm2Params {
   int n_stages;          // ring depth
   int a_sub_bytes, w_sub_bytes, stage_bytes, max_taps;
   int dbg;
+  // optional GroupNorm-apply + SiLU on the A operand (transform warps rewrite the smem tile)
+  const double* gn_stats;   // fp64 [B][gn_groups][2] of the A tensor
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int gn_groups;
 };
 
 struct TileInfo {
@@ -76,6 +82,15 @@ __device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, in
   return ti;
 }
 
+// SiLU with ONE special-function op per element (the transform warps are MUFU-bound):
+// z*sigmoid(z) = 0.5*z*(1 + tanh(z/2)); tanh.approx error (2^-11) is below bf16 rounding.
+__device__ __forceinline__ float silu_tanh(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  const float hz = 0.5f * z;
+  return fmaf(hz, t, hz);
+}
+
 // thread-private GroupNorm partial sums: slot (value v of group g, epilogue thread et)
 struct StatSlots {
   float* base;   // [2*kMaxGroups][128]
@@ -95,8 +110,9 @@ struct StatSlots {
   }
 };
 
-template <int BN, int SW>
-__global__ void __launch_bounds__(192, (BN <= 64 ? 3 : (BN <= 128 ? 2 : 1)))
+template <int BN, int SW, bool XF>
+__global__ void __launch_bounds__(XF ? 448 : 192,
+                                  (BN <= 64 ? (XF ? 2 : 3) : (BN <= 128 ? (XF ? 1 : 2) : 1)))
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const Gemm2Params p) {
   constexpr int BK = SW / 2;
@@ -104,10 +120,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int CH = BN < 32 ? 16 : 32;           // epilogue column chunk
   constexpr uint32_t kWTapBytes = BN * SW;        // bytes one W box writes
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], ready_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[2 * kMaxGroups * 128];
+  __shared__ __align__(16) float s_coef[XF ? 2 * 1024 : 4];   // (a, d) per input channel of the current batch
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -124,7 +141,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tmem_alloc(&tmem_slot, 2 * ACC_COLS);
     tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -184,7 +203,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
         uint32_t accumulate = 0;
         for (int ks = 0; ks < p.k_stages; ++ks) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(XF ? &ready_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           if (!(p.dbg & 1)) {
             const uint64_t sdesc = desc0 + static_cast<uint64_t>(s * stage_u);
@@ -207,7 +226,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(&acc_full[buf]);
       }
     }
-  } else {
+  } else if (warp < 6) {
     // -------------------------------------------------------------------------- epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -337,6 +356,69 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
     if (do_stats && cur_b >= 0) publish_stats(cur_b);
+  } else if constexpr (XF) {
+    // ------------------------------------------------- transform: a = silu(x*ga + de) in place
+    // 256 threads, two per tile row.  The TMA tile is SW-byte rows with the 16-byte chunks
+    // XOR-swizzled by address bits [7, 7+log2(SW/16)); zero rows (conv padding) stay zero.
+    const int tt = threadIdx.x - 192;
+    constexpr int CPR = SW / 16;                 // 16-byte chunks per row
+    constexpr int CPT = CPR / 2 > 0 ? CPR / 2 : 1;   // chunks per thread
+    const int gsz = p.c_in / p.gn_groups;
+    const double inv_n = 1.0 / (static_cast<double>(gsz) * p.T);
+    int s = 0, cur_b = -1;
+    uint32_t ph = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const TileInfo ti = tile_info(p, tile, BN);
+      if (ti.b != cur_b) {     // (a, d) of every input channel for this batch element, once
+        named_bar_sync(3, 256);          // previous batch's coefficients no longer in use
+        for (int ch = tt; ch < p.c_in; ch += 256) {
+          const int g = ch / gsz;
+          const double mean = p.gn_stats[(static_cast<size_t>(ti.b) * p.gn_groups + g) * 2] * inv_n;
+          const float var = fmaxf(static_cast<float>(
+              p.gn_stats[(static_cast<size_t>(ti.b) * p.gn_groups + g) * 2 + 1] * inv_n - mean * mean), 0.f);
+          const float ga = __ldg(p.gn_gamma + ch) * rsqrtf(var + p.gn_eps);
+          s_coef[2 * ch] = ga;
+          s_coef[2 * ch + 1] = __ldg(p.gn_beta + ch) - static_cast<float>(mean) * ga;
+        }
+        named_bar_sync(3, 256);
+        cur_b = ti.b;
+      }
+      for (int ks = 0; ks < p.k_stages; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* st = ring + s * p.stage_bytes;
+        for (int c = 0; c < p.kc; ++c) {
+          uint8_t* sub = st + c * p.a_sub_bytes;
+          const float* cf = s_coef + (ks * p.kc + c) * BK * 2;
+          for (int rr = tt >> 1; rr < p.a_rows; rr += 128) {
+            const int t = ti.t0 + ti.min_off + rr;
+            if (t < 0 || t >= p.T) continue;               // TMA zero fill = conv padding
+            const uint32_t row_off = static_cast<uint32_t>(rr) * SW;
+            const int swz = (row_off >> 7) & (CPR - 1);
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) {
+              const int pc = (CPR >= 2) ? (tt & 1) * CPT + q : 0;      // physical chunk
+              if (CPR < 2 && (tt & 1)) continue;
+              const int lc = pc ^ swz;                                  // logical chunk
+              uint4* ptr = reinterpret_cast<uint4*>(sub + row_off + pc * 16);
+              const uint4 u = *ptr;
+              const float4* c4 = reinterpret_cast<const float4*>(cf + lc * 16);
+              const float4 k0 = c4[0], k1 = c4[1], k2 = c4[2], k3 = c4[3];   // (a,d) x 8 channels
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+              const float2 f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              uint4 o;
+              o.x = pack_bf16(silu_tanh(f0.x * k0.x + k0.y), silu_tanh(f0.y * k0.z + k0.w));
+              o.y = pack_bf16(silu_tanh(f1.x * k1.x + k1.y), silu_tanh(f1.y * k1.z + k1.w));
+              o.z = pack_bf16(silu_tanh(f2.x * k2.x + k2.y), silu_tanh(f2.y * k2.z + k2.w));
+              o.w = pack_bf16(silu_tanh(f3.x * k3.x + k3.y), silu_tanh(f3.y * k3.z + k3.w));
+              *ptr = o;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&ready_bar[s]);
+        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+      }
+    }
   }
 
   tc_fence_before();
@@ -358,7 +440,7 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int SW>
+template <int BN, int SW, bool XF>
 static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   constexpr int BK = SW / 2;
   const int tiles_per_batch = (a.T + kBM - 1) / kBM;
@@ -380,10 +462,11 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   int occ = 1;
   if (BN <= 64 && w_iters <= 8) occ = 3;
   else if (BN <= 128 && w_iters <= 12) occ = 2;
+  if (XF && occ > (BN <= 64 ? 2 : 1)) occ = BN <= 64 ? 2 : 1;
   if (g_debug[3] > 0) occ = g_debug[3];
   const int tmem_occ = 512 / (2 * (BN < 32 ? 32 : BN));
   if (occ > tmem_occ) occ = tmem_occ;
-  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? 100 : 62)) * 1024; };  // 8 KB static smem/CTA
+  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024; };  // 8 KB static smem/CTA
   while (occ > 1 && budget_of(occ) < 2 * chunk_bytes) --occ;   // need >= 2 stages in the ring
   const int budget = budget_of(occ);
   // chunks per stage: amortise one mbarrier round trip over >= 8 MMAs where smem allows
@@ -418,7 +501,7 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
 
   static size_t smem_attr = 0;
   if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW>,
+    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW, XF>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
@@ -448,23 +531,38 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   p.total_tiles = a.B * tiles_per_batch * p.n_tiles_n;
   p.a_rows = a_rows;
   p.dbg = g_debug[4];
+  p.gn_stats = a.gn_stats;
+  p.gn_gamma = a.gn_gamma;
+  p.gn_beta = a.gn_beta;
+  p.gn_eps = a.gn_eps;
+  p.gn_groups = a.gn_groups > 0 ? a.gn_groups : 1;
 
   int grid = p.total_tiles < occ * num_sms() ? p.total_tiles : occ * num_sms();
   p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW>, dim3(grid), dim3(192), smem, stream, tmA, tmW, p));
+  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW, XF>, dim3(grid), dim3(XF ? 448 : 192), smem, stream, tmA,
+                    tmW, p));
   ADP_LAUNCH_CHECK();
   return 0;
 }
 
 template <int SW>
 static int dispatch_bn2(const adp_conv_gemm_args& a, int bn, cudaStream_t s) {
+  if (a.gn_stats) {
+    switch (bn) {
+      case 16: return launch_gemm2<16, SW, true>(a, s);
+      case 32: return launch_gemm2<32, SW, true>(a, s);
+      case 64: return launch_gemm2<64, SW, true>(a, s);
+      case 128: return launch_gemm2<128, SW, true>(a, s);
+      case 256: return launch_gemm2<256, SW, true>(a, s);
+    }
+  }
   switch (bn) {
-    case 16: return launch_gemm2<16, SW>(a, s);
-    case 32: return launch_gemm2<32, SW>(a, s);
-    case 64: return launch_gemm2<64, SW>(a, s);
-    case 128: return launch_gemm2<128, SW>(a, s);
-    case 256: return launch_gemm2<256, SW>(a, s);
+    case 16: return launch_gemm2<16, SW, false>(a, s);
+    case 32: return launch_gemm2<32, SW, false>(a, s);
+    case 64: return launch_gemm2<64, SW, false>(a, s);
+    case 128: return launch_gemm2<128, SW, false>(a, s);
+    case 256: return launch_gemm2<256, SW, false>(a, s);
   }
   return set_error("adp_conv_gemm: unsupported N tile %d", bn);
 }
@@ -508,6 +606,11 @@ extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream
   }
   if (a.out_fp32) {
     ADP_CHECK(!a.residual && !a.stats, "adp_conv_gemm: out_fp32 excludes residual/stats");
+  }
+  if (a.gn_stats) {
+    ADP_CHECK(a.c_in <= 1024, "adp_conv_gemm: fused GroupNorm supports c_in <= 1024");
+    ADP_CHECK(a.gn_gamma && a.gn_beta && a.gn_groups > 0 && a.c_in % a.gn_groups == 0 && a.lda == a.c_in,
+              "adp_conv_gemm: fused GroupNorm needs gamma/beta, groups | c_in and a dense input");
   }
   if (a.stats) {
     ADP_CHECK(a.groups > 0 && a.groups <= kMaxGroups && a.n_valid % a.groups == 0,

@@ -229,6 +229,11 @@ class B200UNet(nn.Module):
         self._packed = None
         self._packed_version = None
         self.use_cuda_graph = True
+        # GroupNorm+SiLU applied inside the conv GEMM by transform warps (adp_conv_gemm gn_*).
+        # Verified bit-compatible with the two-kernel path but measured SLOWER on the README
+        # config (6.85 vs 6.0 ms / evaluation, profiles/r1_gn_fusion.txt): every N tile repeats
+        # the transform of its A rows, so it only pays for N <= BN.  Off by default.
+        self.fuse_groupnorm = False
 
     # ------------------------------------------------------------------ weights
     def levels(self) -> List[LevelParams]:
@@ -445,22 +450,31 @@ class B200UNet(nn.Module):
                         ln_eps=self.MOD_LN_EPS))
                     pool.put(h)
                 else:
-                    a = pool.get(Bh, Tl, C)
                     h = pool.get(Bh, Tl, C)
                     r = pool.get(Bh, Tl, C)
                     y = pool.get(Bh, Tl, C)
-                    plan.add(lambda x=x, a=a, s=x_stats, ip=ip: ops.gn_silu(
-                        x, a, s, ip["gn1"][0], ip["gn1"][1], G, self.GN_EPS))
-                    plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.conv_gemm(
-                        a, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs,
-                        groups=G))
-                    plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.gn_silu(
-                        h, a, hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS))
-                    plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
-                        a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
+                    if self.fuse_groupnorm:
+                        # ConvBlock = ONE kernel: GroupNorm+SiLU applied to the smem A tile
+                        plan.add(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.conv_gemm(
+                            x, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs,
+                            groups=G, gn=(s, ip["gn1"][0], ip["gn1"][1], G, self.GN_EPS)))
+                        plan.add(lambda x=x, h=h, r=r, hs=h_stats, ip=ip: ops.conv_gemm(
+                            h, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x,
+                            gn=(hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS)))
+                    else:
+                        a = pool.get(Bh, Tl, C)
+                        plan.add(lambda x=x, a=a, s=x_stats, ip=ip: ops.gn_silu(
+                            x, a, s, ip["gn1"][0], ip["gn1"][1], G, self.GN_EPS))
+                        plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.conv_gemm(
+                            a, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs,
+                            groups=G))
+                        plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.gn_silu(
+                            h, a, hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS))
+                        plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
+                            a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
+                        pool.put(a)
                     plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats: ops.ln_film(
                         r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS))
-                    pool.put(a)
                     pool.put(h)
                     pool.put(r)
                 # the item's input is dead now (a level's skip is the chain's *output*)

@@ -73,6 +73,13 @@ typedef struct adp_conv_gemm_args {
   int32_t block_n;      /* N tile override (16..256), 0 = auto      */
   int32_t out_fp32;     /* 1: `out` is fp32 [B][T][ldo] (conditioning projections); no residual */
   int32_t ld_gate;      /* row pitch of gate in elements (multiple of 4); 0 = n_valid */
+  /* optional fused prologue: a := SiLU(GroupNorm(a)) applied to the smem tile before the MMAs
+   * (a_unet ConvBlock's GroupNorm + SiLU); gn_stats = fp64 [B][gn_groups][2] of `a`. */
+  const double* gn_stats;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int32_t gn_groups;
 } adp_conv_gemm_args;
 int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream);
 

@@ -344,3 +344,26 @@ def test_attention(ops, B, H, Tq, Tk):
     ref = F.scaled_dot_product_attention(heads(q), heads(k), heads(v))
     ref = ref.transpose(1, 2).reshape(B, Tq, mid)
     assert_close(o, ref, 2 ** -6, 2e-2, f"attention B{B} H{H} Tq{Tq} Tk{Tk}")
+
+
+@pytest.mark.parametrize("B,T,C,co", [(2, 512, 64, 64), (2, 300, 128, 128), (1, 256, 32, 32),
+                                      (2, 100, 256, 256), (1, 128, 16, 16), (2, 1000, 1024, 128),
+                                      (8, 2048, 64, 64)])
+def test_conv_gemm_fused_groupnorm_silu(ops, B, T, C, co):
+    """ConvBlock in one kernel: conv3(SiLU(GroupNorm(x))) with the normalisation applied to the
+    smem A tile by the transform warps (zero padding must stay zero after the activation)."""
+    groups = 8
+    x = bf(rnd(B, T, C, seed=60) * 1.5 + 0.3)
+    gamma, beta = rnd(C, seed=61) * 0.2 + 1.0, rnd(C, seed=62) * 0.2
+    w = bf(rnd(co, C, 3, scale=(3 * C) ** -0.5, seed=63))
+    bias = rnd(co, seed=64)
+    res = bf(rnd(B, T, co, seed=65))
+    stats_x = stats_of(x, groups).contiguous()
+    stats = torch.zeros(B, groups, 2, dtype=torch.float64, device=DEV)
+    out = torch.empty(B, T, co, dtype=torch.bfloat16, device=DEV)
+    ops.conv_gemm(x, ops.pack_conv(w), out, c_in=C, n_valid=co, taps=(-1, 0, 1), bias=bias,
+                  residual=res, stats=stats, groups=groups, gn=(stats_x, gamma, beta, groups, 1e-5))
+    a = bf(F.silu(F.group_norm(x.float().transpose(1, 2), groups, gamma, beta, 1e-5))).float()
+    ref = F.conv1d(a, w.float(), bias, padding=1).transpose(1, 2) + res.float()
+    assert_close(out, ref, 2 ** -6, 3e-2, f"fused gn+silu conv3 C{C}")
+    assert_close(stats, stats_of(out, groups), 1e-4, 1e-2, "fused gn stats")
