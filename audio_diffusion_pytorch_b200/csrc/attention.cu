@@ -48,7 +48,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __shared__ float s_xch[2][kQT];
 
   pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -81,53 +81,65 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform for ptxas
   const uint32_t tmem_s = tmem_base;
   pdl_wait();
   const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 8) {
-    if (lane == 0) {
+    // whole warp runs the loop (uniform control flow), one elected lane issues: see ptx.cuh
+    if (elect_one()) {
       mbar_arrive_expect_tx(&q_full, kQBytes);
       tma_load_3d(q_s, &tmQ, &q_full, h * kD, t0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[s], kKVBytes);
         tma_load_3d(k_s + s * kKVBytes, &tmK, &k_full[s], h * kD, j * kKT, b);
-        mbar_wait(&v_empty, (j & 1) ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty, (j & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full, kKVBytes);
         tma_load_3d(v_s, &tmV, &v_full, h * kD, j * kKT, b);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, 0, 1);   // B (= V) is MN-major
-      mbar_wait(&q_full, 0);
-      const uint64_t q_desc = umma_desc_kmajor<128>(smem_u32(q_s));
-      const uint64_t p_desc = umma_desc_kmajor<128>(smem_u32(p_s));
-      const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(v_s), 1024);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1);
-        tc_fence_after();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(kQT, kKT, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, 0, 1);   // B (= V) is MN-major
+    mbar_wait(&q_full, 0);
+    const uint64_t q_desc = umma_desc_kmajor<128>(smem_u32(q_s));
+    const uint64_t p_desc = umma_desc_kmajor<128>(smem_u32(p_s));
+    const uint64_t v_desc = umma_desc_mnmajor_sw128(smem_u32(v_s), 1024);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      mbar_wait(&k_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t k_desc = umma_desc_kmajor<128>(smem_u32(k_s + s * kKVBytes));
 #pragma unroll
         for (int kk = 0; kk < kD / 16; ++kk)
           umma_bf16(tmem_s, q_desc + ((kk * 32) >> 4), k_desc + ((kk * 32) >> 4), idesc_qk, kk != 0);
         umma_commit(&s_full);
         umma_commit(&k_empty[s]);
-        mbar_wait(&p_full, j & 1);
-        mbar_wait(&v_full, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(&p_full, j & 1);
+      mbar_wait(&v_full, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kKT / 16; ++kk)
           umma_bf16(tmem_o, p_desc + (((kk >> 2) * (kQT * 128) + (kk & 3) * 32) >> 4),
                     v_desc + ((kk * 16 * 128) >> 4), idesc_pv, (j | kk) != 0);
         umma_commit(&v_empty);
+        if (j == n_tiles - 1) umma_commit(&o_done);
       }
-      umma_commit(&o_done);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------- softmax / epilogue

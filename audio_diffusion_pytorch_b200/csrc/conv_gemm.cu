@@ -124,10 +124,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_part[2 * kMaxGroups * 128];
+  // per-tile bias / gate of the BN output columns, double buffered like the accumulators:
+  // staged while the tile's MMAs run so the drain never waits on a global load
+  __shared__ __align__(16) float s_bias[2][BN < 32 ? 32 : BN];
+  __shared__ __align__(16) float s_gate[2][BN < 32 ? 32 : BN];
   __shared__ __align__(16) float s_coef[XF ? 2 * 1024 : 4];   // (a, d) per input channel of the current batch
 
   pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5;
+  if (p.dbg & 8) return;      // timing experiment: launch floor of this configuration
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -152,12 +157,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform for ptxas
   pdl_wait();   // inputs (activations, statistics, conditioning) come from the previous kernel
 
   if (warp == 0) {
     // ---------------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * SW;
@@ -167,25 +172,28 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ks = 0; ks < p.k_stages; ++ks) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = ring + s * p.stage_bytes;
-          if (p.dbg & 2) {
-            mbar_arrive(&full_bar[s]);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], tx);
-            for (int c = 0; c < p.kc; ++c) {
-              const int k0 = (ks * p.kc + c) * BK;
-              tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
-              uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
-              for (int tap = 0; tap < ti.ntaps; ++tap)
-                tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
+          if (elect_one()) {
+            if (p.dbg & 2) {
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], tx);
+              for (int c = 0; c < p.kc; ++c) {
+                const int k0 = (ks * p.kc + c) * BK;
+                tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
+                uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
+                for (int tap = 0; tap < ti.ntaps; ++tap)
+                  tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
+              }
             }
           }
+          __syncwarp();
           if (++s == p.n_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
       // descriptor of the ring base; byte offsets are added to the 14-bit address field
       const uint64_t desc0 = umma_desc_kmajor<SW>(smem_u32(ring));
@@ -205,25 +213,29 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int ks = 0; ks < p.k_stages; ++ks) {
           mbar_wait(XF ? &ready_bar[s] : &full_bar[s], ph);
           tc_fence_after();
-          if (!(p.dbg & 1)) {
-            const uint64_t sdesc = desc0 + static_cast<uint64_t>(s * stage_u);
-            for (int c = 0; c < p.kc; ++c) {
-              const uint64_t adesc = sdesc + c * a_sub_u;
-              const uint64_t wdesc = sdesc + w_base_u + c * p.max_taps * w_sub_u;
-              for (int tap = 0; tap < ti.ntaps; ++tap) {
+          if (elect_one()) {        // ONE elected thread issues the whole stage and its commit
+            if (!(p.dbg & 1)) {
+              const uint64_t sdesc = desc0 + static_cast<uint64_t>(s * stage_u);
+              for (int c = 0; c < p.kc; ++c) {
+                const uint64_t adesc = sdesc + c * a_sub_u;
+                const uint64_t wdesc = sdesc + w_base_u + c * p.max_taps * w_sub_u;
+                for (int tap = 0; tap < ti.ntaps; ++tap) {
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; ++kk) {
-                  umma_bf16(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
-                            wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
-                  accumulate = 1;
+                  for (int kk = 0; kk < BK / 16; ++kk) {
+                    umma_bf16(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
+                              wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
+                    accumulate = 1;
+                  }
                 }
               }
             }
+            umma_commit(&empty_bar[s]);
+            if (ks == p.k_stages - 1) umma_commit(&acc_full[buf]);
           }
-          umma_commit(&empty_bar[s]);
+          accumulate = 1;
+          __syncwarp();
           if (++s == p.n_stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&acc_full[buf]);
       }
     }
   } else if (warp < 6) {
@@ -241,11 +253,13 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       acc.flush();
       acc.cur_g = -1;
       named_bar_sync(1, 128);
-      if (et < 2 * p.groups) {
-        float tot = 0.f;
-        for (int i = 0; i < 128; ++i) tot += s_part[et * 128 + ((i + et) & 127)];
-        if (tot != 0.f)
-          atomicAdd(p.stats + static_cast<size_t>(b_done) * 2 * p.groups + et,
+      for (int r2 = q; r2 < 2 * p.groups; r2 += 4) {     // warp q reduces rows q, q+4, ...
+        const float* rowp = s_part + r2 * 128 + lane;
+        float tot = (rowp[0] + rowp[32]) + (rowp[64] + rowp[96]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0 && tot != 0.f)
+          atomicAdd(p.stats + static_cast<size_t>(b_done) * 2 * p.groups + r2,
                     static_cast<double>(tot));
       }
       named_bar_sync(1, 128);
@@ -274,11 +288,19 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             res[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + row_off + ch));
         }
       }
+      for (int c = et; c < BN; c += 128) {
+        const int ch = ti.ch0 + c;
+        const bool ok = ch < p.n_valid;
+        s_bias[buf][c] = (p.bias && ok) ? __ldg(p.bias + ch) : 0.f;
+        s_gate[buf][c] = (p.gate && ok) ? __ldg(p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch) : 1.f;
+      }
+      named_bar_sync(2, 128);     // staging visible to the four epilogue warps
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * ACC_COLS + lane_addr;
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += CH) {
+        if (p.dbg & 4) break;   // timing experiment: skip the drain
         uint32_t r[CH];
         if constexpr (CH == 16) tmem_ld16(taddr + c0, r);
         else tmem_ld32(taddr + c0, r);
@@ -290,16 +312,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[v8 * 8 + i]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch + 4));
+          {
+            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[buf][c0 + v8 * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[buf][c0 + v8 * 8 + 4]);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
           if (p.gate) {
-            const float* gp = p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch;
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+            const float4 g0 = *reinterpret_cast<const float4*>(&s_gate[buf][c0 + v8 * 8]);
+            const float4 g1 = *reinterpret_cast<const float4*>(&s_gate[buf][c0 + v8 * 8 + 4]);
             v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
             v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
           }
@@ -466,7 +487,7 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   if (g_debug[3] > 0) occ = g_debug[3];
   const int tmem_occ = 512 / (2 * (BN < 32 ? 32 : BN));
   if (occ > tmem_occ) occ = tmem_occ;
-  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024; };  // 8 KB static smem/CTA
+  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024; };  // <= 11 KB static smem/CTA
   while (occ > 1 && budget_of(occ) < 2 * chunk_bytes) --occ;   // need >= 2 stages in the ring
   const int budget = budget_of(occ);
   // chunks per stage: amortise one mbarrier round trip over >= 8 MMAs where smem allows

@@ -13,6 +13,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Warp-uniform helpers.  The TMA / MMA issue loops are executed by the WHOLE warp with only the
+// instruction itself under elect_one(): inside an `if (lane == 0)` region ptxas cannot prove
+// the descriptor operands uniform and wraps every UTCHMMA / UTMALDG in an R2UR waterfall loop
+// (~100 cycles per MMA); with uniform control flow they stay in uniform registers.
+__device__ __forceinline__ int warp_id_uniform() {
+  return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -214,6 +231,14 @@ __device__ __forceinline__ void pdl_wait() {
 
 // -------------------------------------------------------------------------------- misc
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// SiLU with ONE special-function op: z*sigmoid(z) = 0.5*z*(1 + tanh(z/2)).  tanh.approx is
+// accurate to ~2^-11, i.e. below the bf16 rounding applied to the result by every caller.
+__device__ __forceinline__ float silu_fast(float z) {
+  float t;
+  const float hz = 0.5f * z;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hz));
+  return fmaf(hz, t, hz);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }

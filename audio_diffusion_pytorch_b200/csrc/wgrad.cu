@@ -40,7 +40,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   __shared__ uint32_t tmem_slot;
 
   pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -64,17 +64,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform for ptxas
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int c = chunk_begin; c < chunk_end; ++c) {
-        const int b = c / p.chunks_per_batch;
-        const int t0 = (c - b * p.chunks_per_batch) * kWgChunk;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // whole warp runs the loop (uniform control flow), one elected lane issues: see ptx.cuh
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = chunk_begin; c < chunk_end; ++c) {
+      const int b = c / p.chunks_per_batch;
+      const int t0 = (c - b * p.chunks_per_batch) * kWgChunk;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* st = ring + s * STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
         tma_load_3d(st, &tmG, &full_bar[s], p.g_col0 + n0, t0, b);
@@ -83,32 +84,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         for (int i = 0; i < NB; ++i)
           tma_load_3d(st + (2 + i) * kWgBoxBytes, &tmX, &full_bar[s], p.x_col0 + k0 + i * 64,
                       t0 + p.off, b);
-        if (++s == p.n_stages) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == p.n_stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
-      // MN-major SW128: 64-channel chunks kWgBoxBytes apart (LBO), 8-row groups 1024 B (SBO)
-      const uint64_t desc0 = umma_desc_mnmajor_sw128(smem_u32(ring), kWgBoxBytes);
-      int s = 0;
-      uint32_t ph = 0, accumulate = 0;
-      for (int c = chunk_begin; c < chunk_end; ++c) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
+    // MN-major SW128: 64-channel chunks kWgBoxBytes apart (LBO), 8-row groups 1024 B (SBO)
+    const uint64_t desc0 = umma_desc_mnmajor_sw128(smem_u32(ring), kWgBoxBytes);
+    int s = 0;
+    uint32_t ph = 0, accumulate = 0;
+    for (int c = chunk_begin; c < chunk_end; ++c) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t gdesc = desc0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
         const uint64_t xdesc = gdesc + ((2 * kWgBoxBytes) >> 4);
 #pragma unroll
         for (int kk = 0; kk < kWgChunk / 16; ++kk) {      // 16 time steps per MMA = 2048 B
           umma_bf16(tmem_base, gdesc + ((kk * 2048) >> 4), xdesc + ((kk * 2048) >> 4), idesc,
-                    accumulate);
-          accumulate = 1;
+                    accumulate | (kk != 0));
         }
         umma_commit(&empty_bar[s]);
-        if (++s == p.n_stages) { s = 0; ph ^= 1; }
+        if (c == chunk_end - 1) umma_commit(&acc_full);
       }
-      umma_commit(&acc_full);
+      accumulate = 1;
+      __syncwarp();
+      if (++s == p.n_stages) { s = 0; ph ^= 1; }
     }
+    // an empty split still has to release the epilogue
+    if (chunk_end <= chunk_begin && elect_one()) umma_commit(&acc_full);
   } else {
     mbar_wait(&acc_full, 0);
     tc_fence_after();

@@ -316,7 +316,9 @@ def test_narrow_conv(ops, film, res):
         ref = ref + resid.float()
     if film:
         ref = F.layer_norm(ref, (C,), eps=1e-6) * (1 + ss[:, None, :C]) + ss[:, None, C:]
-    assert_close(y, ref, 2 ** -7, 1e-2, f"narrow_conv film={film}")
+    # activations AND weights enter the tensor core as bf16 (like every wider level), and the
+    # LayerNorm of the film variant rescales the error by 1/std of an 8-channel row
+    assert_close(y, ref, 2 ** -7, 3e-2 if film else 1e-2, f"narrow_conv film={film}")
     assert_close(stats_out, stats_of(y, groups), 1e-4, 1e-2, "narrow_conv stats")
 
 

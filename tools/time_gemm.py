@@ -31,20 +31,21 @@ def run(M, K, N, taps, bn, res=True, stats=False, B=8, reps=20):
     fl = 2.0 * M * K * N * taps
     return us, fl / us / 1e6
 
-shapes = [("L1 conv3", 524288, 32, 32, 3), ("L7 conv3", 2048, 1024, 1024, 3), ("L8 conv3", 1024, 1024, 1024, 3), ("L5 conv3", 8192, 512, 512, 3),
-          ("L4 conv3", 16384, 256, 256, 3), ("L3 conv3", 32768, 128, 128, 3), ("L2 conv3", 131072, 64, 64, 3),
-          ("L7 qkv", 2048, 1024, 1536, 1), ("L5 qkv", 8192, 512, 1536, 1)]
-modes = [("v1", 1, 1, 0, 0), ("v3", 2, 1, 0, 0), ("noMMA", 2, 1, 0, 1), ("noLOAD", 2, 1, 0, 2), ("neither", 2, 1, 0, 3)]
-for name, M, K, N, taps in shapes:
-    for bn in (32, 64, 128):
-        if N % max(bn, 16): continue
-        if bn > N: continue
-        row = []
-        for mname, impl, single, occ, dbg in modes:
-            L.adp_debug_set(0, impl); L.adp_debug_set(1, single); L.adp_debug_set(3, occ); L.adp_debug_set(4, dbg)
-            try:
-                us, tf = run(M, K, N, taps, bn, res=False, stats=False)
-                row.append(f"{mname}: {us:6.1f}us {tf:5.0f}TF")
-            except Exception as e:
-                row.append(f"{mname}: ERR {str(e)[:40]}")
-        print(f"{name:9s} bn={bn:3d} | " + " | ".join(row), flush=True)
+if __name__ == "__main__":
+    shapes = [("L1 conv3", 524288, 32, 32, 3), ("L7 conv3", 2048, 1024, 1024, 3), ("L8 conv3", 1024, 1024, 1024, 3), ("L5 conv3", 8192, 512, 512, 3),
+              ("L4 conv3", 16384, 256, 256, 3), ("L3 conv3", 32768, 128, 128, 3), ("L2 conv3", 131072, 64, 64, 3),
+              ("L7 qkv", 2048, 1024, 1536, 1), ("L5 qkv", 8192, 512, 1536, 1)]
+    modes = [("v1", 1, 1, 0, 0), ("v3", 2, 1, 0, 0), ("noMMA", 2, 1, 0, 1), ("noLOAD", 2, 1, 0, 2), ("neither", 2, 1, 0, 3)]
+    for name, M, K, N, taps in shapes:
+        for bn in (32, 64, 128):
+            if N % max(bn, 16): continue
+            if bn > N: continue
+            row = []
+            for mname, impl, single, occ, dbg in modes:
+                L.adp_debug_set(0, impl); L.adp_debug_set(1, single); L.adp_debug_set(3, occ); L.adp_debug_set(4, dbg)
+                try:
+                    us, tf = run(M, K, N, taps, bn, res=False, stats=False)
+                    row.append(f"{mname}: {us:6.1f}us {tf:5.0f}TF")
+                except Exception as e:
+                    row.append(f"{mname}: ERR {str(e)[:40]}")
+            print(f"{name:9s} bn={bn:3d} | " + " | ".join(row), flush=True)
