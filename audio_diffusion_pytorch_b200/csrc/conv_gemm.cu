@@ -25,7 +25,8 @@ namespace adp {
 int conv_gemm_v1(const adp_conv_gemm_args* args, adp_stream_t stream);
 
 // A/B + diagnostic switches (adp_debug_set): [0] impl 2=persistent 1=v1; [3] CTAs/SM override;
-// [4] bit0 skip MMAs, bit1 skip TMA loads (timing experiments only); [5] KC override
+// [4] bit0 skip MMAs, bit1 skip TMA loads, bit2 skip drain, bit3 exit at entry (timing
+// experiments only); [5] KC override; [6] PDL; [7] 1 = never use the 8-epilogue-warp variant
 int g_debug[8] = {2, 1, 0, 0, 0, 0, 0, 0};
 
 constexpr int kBM = 128;
@@ -92,15 +93,16 @@ __device__ __forceinline__ float silu_tanh(float z) {
 }
 
 // thread-private GroupNorm partial sums: slot (value v of group g, epilogue thread et)
+template <int NET>      // NET = epilogue threads per CTA
 struct StatSlots {
-  float* base;   // [2*kMaxGroups][128]
+  float* base;   // [2*kMaxGroups][NET]
   int et;
   int cur_g;
   float s, q;
   __device__ __forceinline__ void flush() {
     if (cur_g >= 0) {
-      base[(2 * cur_g) * 128 + et] += s;
-      base[(2 * cur_g + 1) * 128 + et] += q;
+      base[(2 * cur_g) * NET + et] += s;
+      base[(2 * cur_g + 1) * NET + et] += q;
     }
     s = 0.f; q = 0.f;
   }
@@ -110,9 +112,25 @@ struct StatSlots {
   }
 };
 
-template <int BN, int SW, bool XF>
-__global__ void __launch_bounds__(XF ? 448 : 192,
-                                  (BN <= 64 ? (XF ? 2 : 3) : (BN <= 128 ? (XF ? 1 : 2) : 1)))
+// GroupNorm partial sums for group sizes that are neither >= 8 nor 4 (never the case in the
+// reference configurations): straight into the thread-private slots, one element at a time.
+static __device__ __noinline__ void stats_generic(float* slots, int net, int et, int ch, int shift,
+                                                  int gsize, float v0, float v1, float v2, float v3,
+                                                  float v4, float v5, float v6, float v7) {
+  const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+  for (int i = 0; i < 8; ++i) {
+    const int g = shift >= 0 ? (ch + i) >> shift : (ch + i) / gsize;
+    slots[(2 * g) * net + et] += v[i];
+    slots[(2 * g + 1) * net + et] += v[i] * v[i];
+  }
+}
+
+// EW = epilogue warps: 4 (one per TMEM lane quarter) or, for the long-K shapes that run one CTA
+// per SM with <= one tile per CTA (nothing to overlap the drain with), 8: two warps per lane
+// quarter, each draining half of the tile's columns.
+template <int BN, int SW, bool XF, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW + (XF ? 256 : 0),
+                                  EW == 8 ? 1 : (BN <= 64 ? (XF ? 2 : 3) : (BN <= 128 ? (XF ? 1 : 2) : 1)))
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const Gemm2Params p) {
   constexpr int BK = SW / 2;
@@ -123,7 +141,11 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], ready_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_part[2 * kMaxGroups * 128];
+  constexpr int NET = 32 * EW;                    // epilogue threads
+  constexpr int BNW = BN / (EW / 4);              // columns drained by one epilogue warp
+  static_assert(!XF || EW == 4, "the transform variant runs four epilogue warps");
+  static_assert(EW == 4 || BNW >= 32, "8 epilogue warps need >= 32 columns per warp");
+  __shared__ float s_part[2 * kMaxGroups * NET];
   // per-tile bias / gate of the BN output columns, double buffered like the accumulators:
   // staged while the tile's MMAs run so the drain never waits on a global load
   __shared__ __align__(16) float s_bias[2][BN < 32 ? 32 : BN];
@@ -141,7 +163,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   int tile_end = tile_begin + p.tiles_per_cta;
   if (tile_end > p.total_tiles) tile_end = p.total_tiles;
 
-  for (int i = threadIdx.x; i < 2 * kMaxGroups * 128; i += blockDim.x) s_part[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * kMaxGroups * NET; i += blockDim.x) s_part[i] = 0.f;
   if (warp == 0) {
     tmem_alloc(&tmem_slot, 2 * ACC_COLS);
     tmem_relinquish();
@@ -149,7 +171,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -238,32 +260,35 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + EW) {
     // -------------------------------------------------------------------------- epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const bool do_stats = p.stats != nullptr;
-    const int et = threadIdx.x - 64;        // 0..127 among epilogue threads
-    StatSlots acc{s_part, et, -1, 0.f, 0.f};
+    const int et = threadIdx.x - 64;        // 0..NET-1 among epilogue threads
+    const int cbeg = ((warp - 2) >> 2) * BNW;   // first tile column of this warp
+    StatSlots<NET> acc{s_part, et, -1, 0.f, 0.f};
     int cur_b = -1;
     uint32_t j = 0;
 
     auto publish_stats = [&](int b_done) {   // all 128 epilogue threads
       acc.flush();
       acc.cur_g = -1;
-      named_bar_sync(1, 128);
-      for (int r2 = q; r2 < 2 * p.groups; r2 += 4) {     // warp q reduces rows q, q+4, ...
-        const float* rowp = s_part + r2 * 128 + lane;
-        float tot = (rowp[0] + rowp[32]) + (rowp[64] + rowp[96]);
+      named_bar_sync(1, NET);
+      for (int r2 = warp - 2; r2 < 2 * p.groups; r2 += EW) {     // one warp per row of slots
+        const float* rowp = s_part + r2 * NET + lane;
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < EW; ++i) tot += rowp[32 * i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0 && tot != 0.f)
           atomicAdd(p.stats + static_cast<size_t>(b_done) * 2 * p.groups + r2,
                     static_cast<double>(tot));
       }
-      named_bar_sync(1, 128);
-      for (int g2 = 0; g2 < 2 * p.groups; ++g2) s_part[g2 * 128 + et] = 0.f;
+      named_bar_sync(1, NET);
+      for (int g2 = 0; g2 < 2 * p.groups; ++g2) s_part[g2 * NET + et] = 0.f;
     };
 
     for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
@@ -278,28 +303,29 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         cur_b = ti.b;
       }
       // residual rows of this tile -> registers, while the tile's MMAs are still running
-      uint4 res[BN / 8];
+      uint4 res[BNW / 8];
       if (p.residual) {
 #pragma unroll
-        for (int i = 0; i < BN / 8; ++i) {
-          const int ch = ti.ch0 + i * 8;
+        for (int i = 0; i < BNW / 8; ++i) {
+          const int ch = ti.ch0 + cbeg + i * 8;
           res[i] = make_uint4(0, 0, 0, 0);
           if (row_ok && ch < p.n_valid)
             res[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + row_off + ch));
         }
       }
-      for (int c = et; c < BN; c += 128) {
+      for (int c = et; c < BN; c += NET) {
         const int ch = ti.ch0 + c;
         const bool ok = ch < p.n_valid;
         s_bias[buf][c] = (p.bias && ok) ? __ldg(p.bias + ch) : 0.f;
         s_gate[buf][c] = (p.gate && ok) ? __ldg(p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch) : 1.f;
       }
-      named_bar_sync(2, 128);     // staging visible to the four epilogue warps
+      named_bar_sync(2, NET);     // staging visible to all epilogue warps
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * ACC_COLS + lane_addr;
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int cc = 0; cc < BNW; cc += CH) {
+        const int c0 = cbeg + cc;
         if (p.dbg & 4) break;   // timing experiment: skip the drain
         uint32_t r[CH];
         if constexpr (CH == 16) tmem_ld16(taddr + c0, r);
@@ -334,7 +360,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (row_ok) {
             if (p.residual) {
-              const uint4 rr = res[(c0 + v8 * 8) / 8];
+              const uint4 rr = res[(cc + v8 * 8) / 8];
               const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y);
               const float2 r2 = unpack_bf16(rr.z), r3 = unpack_bf16(rr.w);
               v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
@@ -362,11 +388,18 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int g = ch >> p.group_shift;
               if (g != acc.cur_g) { acc.flush(); acc.cur_g = g; }
               acc.s += s8; acc.q += q8;
+            } else if (p.group_shift == 2) {   // 4-channel groups: the vector spans g and g + 1
+              const int g = ch >> 2;
+              float* lo = s_part + (2 * g) * NET + et;
+              lo[0] += (v[0] + v[1]) + (v[2] + v[3]);
+              lo[NET] += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+              lo[2 * NET] += (v[4] + v[5]) + (v[6] + v[7]);
+              lo[3 * NET] += (v[4] * v[4] + v[5] * v[5]) + (v[6] * v[6] + v[7] * v[7]);
             } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                acc.add(v[i], p.group_shift >= 0 ? (ch + i) >> p.group_shift
-                                                 : (ch + i) / p.group_size);
+              // rare group sizes: out of line, or this code is unrolled BN/8 times into the
+              // drain loop and the epilogue stalls on instruction fetch
+              stats_generic(s_part, NET, et, ch, p.group_shift, p.group_size, v[0], v[1], v[2], v[3],
+                            v[4], v[5], v[6], v[7]);
             }
           }
         }
@@ -381,7 +414,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------- transform: a = silu(x*ga + de) in place
     // 256 threads, two per tile row.  The TMA tile is SW-byte rows with the 16-byte chunks
     // XOR-swizzled by address bits [7, 7+log2(SW/16)); zero rows (conv padding) stay zero.
-    const int tt = threadIdx.x - 192;
+    const int tt = threadIdx.x - (64 + NET);
     constexpr int CPR = SW / 16;                 // 16-byte chunks per row
     constexpr int CPT = CPR / 2 > 0 ? CPR / 2 : 1;   // chunks per thread
     const int gsz = p.c_in / p.gn_groups;
@@ -461,8 +494,16 @@ static int num_sms() {
   return n;
 }
 
+template <int BN, int SW, bool XF, int EW>
+static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int occ_in);
+
 template <int BN, int SW, bool XF>
 static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
+  return launch_gemm2_ew<BN, SW, XF, 4>(a, stream, 0);
+}
+
+template <int BN, int SW, bool XF, int EW>
+static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int occ_in) {
   constexpr int BK = SW / 2;
   const int tiles_per_batch = (a.T + kBM - 1) / kBM;
   const bool up = a.up_factor > 1;
@@ -485,10 +526,20 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   else if (BN <= 128 && w_iters <= 12) occ = 2;
   if (XF && occ > (BN <= 64 ? 2 : 1)) occ = BN <= 64 ? 2 : 1;
   if (g_debug[3] > 0) occ = g_debug[3];
+  if (occ_in > 0) occ = occ_in;
   const int tmem_occ = 512 / (2 * (BN < 32 ? 32 : BN));
   if (occ > tmem_occ) occ = tmem_occ;
-  auto budget_of = [](int o) { return (o == 1 ? 196 : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024; };  // <= 11 KB static smem/CTA
+  auto budget_of = [](int o) {
+    return (o == 1 ? (EW == 8 ? 204 : 196) : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024;   // 227 KB - static - 1 KB
+  };  // <= 11 KB static smem/CTA
   while (occ > 1 && budget_of(occ) < 2 * chunk_bytes) --occ;   // need >= 2 stages in the ring
+  if constexpr (EW == 4 && !XF && BN >= 64) {
+    // at most ~two tiles per SM: little or nothing overlaps the drain -> one CTA per SM with
+    // 8 drain warps (also when 2 CTAs/SM were possible but every SM gets <= one tile anyway)
+    const long total = (long)a.B * tiles_per_batch * (a.phases * a.n_pad / BN);
+    if (g_debug[7] == 0 && ((occ == 1 && total <= 2L * num_sms()) || total <= (long)num_sms()))
+      return launch_gemm2_ew<BN, SW, XF, 8>(a, stream, 1);
+  }
   const int budget = budget_of(occ);
   // chunks per stage: amortise one mbarrier round trip over >= 8 MMAs where smem allows
   int kc = 1;
@@ -522,7 +573,7 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
 
   static size_t smem_attr = 0;
   if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW, XF>,
+    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW, XF, EW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
@@ -561,7 +612,7 @@ static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
   int grid = p.total_tiles < occ * num_sms() ? p.total_tiles : occ * num_sms();
   p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW, XF>, dim3(grid), dim3(XF ? 448 : 192), smem, stream, tmA,
+  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW, XF, EW>, dim3(grid), dim3(64 + 32 * EW + (XF ? 256 : 0)), smem, stream, tmA,
                     tmW, p));
   ADP_LAUNCH_CHECK();
   return 0;

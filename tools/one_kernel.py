@@ -1,5 +1,5 @@
 """Launches one kernel shape repeatedly (for `ncu --set full`).
-usage: python tools/one_kernel.py conv M K N taps [block_n] | attn B H T | lnfilm B T C | gnsilu B T C"""
+usage: python tools/one_kernel.py conv M K N taps [block_n [stats]] | attn B H T | lnfilm B T C | gnsilu B T C"""
 import os
 import sys
 
@@ -15,6 +15,7 @@ reps = 6
 if kind == "conv":
     M, K, N, taps = a[:4]
     bn = a[4] if len(a) > 4 else 0
+    with_stats = len(a) > 5 and a[5] != 0
     B = 8
     x = torch.randn(B, M // B, K, device=dev).bfloat16()
     w = torch.randn(N, K, taps, device=dev) * (K * taps) ** -0.5
@@ -23,8 +24,9 @@ if kind == "conv":
     bias = torch.randn(N, device=dev)
     wp = ops.pack_conv(w)
     tp = (-1, 0, 1) if taps == 3 else (0,)
+    st = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64) if with_stats else None
     for _ in range(reps):
-        ops.conv_gemm(x, wp, out, c_in=K, n_valid=N, taps=tp, bias=bias, residual=res, block_n=bn)
+        ops.conv_gemm(x, wp, out, c_in=K, n_valid=N, taps=tp, bias=bias, residual=res, stats=st, block_n=bn)
 elif kind == "attn":
     B, H, T = a
     qkv = torch.randn(B, T, 3 * H * 64, device=dev).bfloat16()
