@@ -17,6 +17,8 @@
 // quarter = warp & 3).  The epilogue prefetches the residual rows of its tile into registers
 // while the tile's MMAs still run, and keeps GroupNorm partial sums in thread-private smem
 // slots (no shuffles / atomics per tile; one reduction per batch change).
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -323,8 +325,70 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * ACC_COLS + lane_addr;
+      // Specialised drains for the shapes the network launches (bias, optional residual and
+      // statistics with >= 8-channel groups, every column valid): the generic loop below pays
+      // ~25 instructions of run-time flag tests per 8-channel vector, and the drain of a
+      // short-K tile is issue/fetch bound.
+      auto drain_fast = [&](auto res_c, auto st_c) {
+        constexpr bool RES = decltype(res_c)::value;
+        constexpr bool ST = decltype(st_c)::value;
+#pragma unroll
+        for (int cc = 0; cc < BNW; cc += CH) {
+          const int c0 = cbeg + cc;
+          uint32_t r[CH];
+          if constexpr (CH == 16) tmem_ld16(taddr + c0, r);
+          else tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int v8 = 0; v8 < CH / 8; ++v8) {
+            const int ch = ti.ch0 + c0 + v8 * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[buf][c0 + v8 * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[buf][c0 + v8 * 8 + 4]);
+            float v[8];
+            v[0] = __uint_as_float(r[v8 * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[v8 * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(r[v8 * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[v8 * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(r[v8 * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[v8 * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(r[v8 * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[v8 * 8 + 7]) + b1.w;
+            if constexpr (RES) {
+              const uint4 rr = res[(cc + v8 * 8) / 8];
+              const float2 r0 = unpack_bf16(rr.x), r1 = unpack_bf16(rr.y);
+              const float2 r2 = unpack_bf16(rr.z), r3 = unpack_bf16(rr.w);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+              v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            }
+            uint4 o;
+            o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+            o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+            if (row_ok) {
+              *reinterpret_cast<uint4*>(p.out + row_off + ch) = o;
+              if constexpr (ST) {      // statistics of the ROUNDED values the next layer reads
+                const float2 q0 = unpack_bf16(o.x), q1 = unpack_bf16(o.y);
+                const float2 q2 = unpack_bf16(o.z), q3 = unpack_bf16(o.w);
+                const float s8 = ((q0.x + q0.y) + (q1.x + q1.y)) + ((q2.x + q2.y) + (q3.x + q3.y));
+                const float q8 = ((q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y)) +
+                                 ((q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y));
+                const int g = ch >> p.group_shift;
+                if (g != acc.cur_g) { acc.flush(); acc.cur_g = g; }
+                acc.s += s8; acc.q += q8;
+              }
+            }
+          }
+        }
+      };
+      const bool fast = !p.gate && !p.out_fp32 && !(p.dbg & 4) && ti.ch0 + cbeg + BNW <= p.n_valid &&
+                        (!do_stats || p.group_shift >= 3);
+      if (fast) {
+        if (p.residual) {
+          if (do_stats) drain_fast(std::true_type{}, std::true_type{});
+          else drain_fast(std::true_type{}, std::false_type{});
+        } else {
+          if (do_stats) drain_fast(std::false_type{}, std::true_type{});
+          else drain_fast(std::false_type{}, std::false_type{});
+        }
+      }
 #pragma unroll
       for (int cc = 0; cc < BNW; cc += CH) {
+        if (fast) break;
         const int c0 = cbeg + cc;
         if (p.dbg & 4) break;   // timing experiment: skip the drain
         uint32_t r[CH];

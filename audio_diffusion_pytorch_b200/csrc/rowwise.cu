@@ -18,10 +18,23 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
                int groups, float eps) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_a[kMaxC];
-  __shared__ float s_d[kMaxC];
+  __shared__ __align__(16) float s_a[kMaxC];
+  __shared__ __align__(16) float s_d[kMaxC];
   const int b = blockIdx.y;
   const int gsz = C / groups;
+  const int vpr = C >> 3;  // vectors per row
+  const uint32_t nvec = static_cast<uint32_t>(T) * vpr;          // < 2^31 (checked by the host)
+  const uint4* xb = x + static_cast<size_t>(b) * nvec;
+  uint4* yb = y + static_cast<size_t>(b) * nvec;
+  // first tile's loads go out BEFORE the coefficients are derived from the statistics: the two
+  // global-latency chains of this (latency-bound at the deep levels) kernel overlap
+  uint4 u[4];
+  uint32_t base = blockIdx.x * 1024u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t i = base + k * 256 + threadIdx.x;
+    u[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
+  }
   const double inv_n = 1.0 / (static_cast<double>(gsz) * T);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / gsz;
@@ -34,34 +47,36 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
     s_d[c] = beta[c] - static_cast<float>(mean) * a;
   }
   __syncthreads();
-  const int vpr = C >> 3;  // vectors per row
-  const size_t nvec = static_cast<size_t>(T) * vpr;
-  const uint4* xb = x + static_cast<size_t>(b) * nvec;
-  uint4* yb = y + static_cast<size_t>(b) * nvec;
-  for (size_t base = static_cast<size_t>(blockIdx.x) * 1024; base < nvec;
-       base += static_cast<size_t>(gridDim.x) * 1024) {
-    uint4 u[4];
+  for (; base < nvec; base += gridDim.x * 1024u) {
+    const uint32_t nbase = base + gridDim.x * 1024u;
+    uint4 un[4];
+    if (nbase < nvec) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t i = base + k * 256 + threadIdx.x;
-      u[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t i = base + k * 256 + threadIdx.x;
-      if (i >= nvec) continue;
-      const int c = static_cast<int>(i % vpr) << 3;
-      const uint32_t in[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-      uint32_t o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16(in[j]);
-        const float v0 = silu_f(f.x * s_a[c + 2 * j] + s_d[c + 2 * j]);
-        const float v1 = silu_f(f.y * s_a[c + 2 * j + 1] + s_d[c + 2 * j + 1]);
-        o[j] = pack_bf16(v0, v1);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = nbase + k * 256 + threadIdx.x;
+        un[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
       }
-      yb[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = base + k * 256 + threadIdx.x;
+      if (i >= nvec) continue;
+      const int c = static_cast<int>(i % static_cast<uint32_t>(vpr)) << 3;
+      const float4 a0 = *reinterpret_cast<const float4*>(&s_a[c]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&s_a[c + 4]);
+      const float4 d0 = *reinterpret_cast<const float4*>(&s_d[c]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&s_d[c + 4]);
+      const float2 f0 = unpack_bf16(u[k].x), f1 = unpack_bf16(u[k].y);
+      const float2 f2 = unpack_bf16(u[k].z), f3 = unpack_bf16(u[k].w);
+      uint4 o;
+      o.x = pack_bf16(silu_f(f0.x * a0.x + d0.x), silu_f(f0.y * a0.y + d0.y));
+      o.y = pack_bf16(silu_f(f1.x * a0.z + d0.z), silu_f(f1.y * a0.w + d0.w));
+      o.z = pack_bf16(silu_f(f2.x * a1.x + d1.x), silu_f(f2.y * a1.y + d1.y));
+      o.w = pack_bf16(silu_f(f3.x * a1.z + d1.z), silu_f(f3.y * a1.w + d1.w));
+      yb[i] = o;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = un[k];
   }
 }
 
@@ -136,11 +151,6 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
   const int gsz = groups > 0 ? C / groups : C;
   const bool do_stats = stats != nullptr;
   if (threadIdx.x < 128) s_acc[threadIdx.x] = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // FiLM coefficients of this batch row
-    s_fs[c] = ss ? 1.f + ss[static_cast<size_t>(b) * ss_stride + c] : 1.f;
-    s_ft[c] = ss ? ss[static_cast<size_t>(b) * ss_stride + C + c] : 0.f;
-  }
-  __syncthreads();
 
   constexpr int NACC = PER_CH ? 8 : VPL;
   float as[NACC], aq[NACC];
@@ -151,18 +161,31 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
   uint4* yb = y + static_cast<size_t>(b) * T * vpr;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const float inv_c = 1.f / static_cast<float>(C);
-  for (int base = (blockIdx.x * (blockDim.x >> 5) + warp) * rpw * UNR; base < T;
-       base += warps_total * rpw * UNR) {
-    uint4 u[UNR][VPL];
+  const int step = warps_total * rpw * UNR;
+  auto load_rows = [&](int base, uint4 (&dst)[UNR][VPL]) {
 #pragma unroll
     for (int un = 0; un < UNR; ++un) {
       const int row = base + un * rpw + sub;
 #pragma unroll
       for (int it = 0; it < VPL; ++it) {
-        u[un][it] = make_uint4(0, 0, 0, 0);
-        if (row < T) u[un][it] = __ldg(xb + static_cast<size_t>(row) * vpr + it * lpr + l);
+        dst[un][it] = make_uint4(0, 0, 0, 0);
+        if (row < T) dst[un][it] = __ldg(xb + static_cast<size_t>(row) * vpr + it * lpr + l);
       }
     }
+  };
+  // the first rows are requested BEFORE the FiLM coefficients are staged (the two global
+  // latencies of this latency-bound kernel overlap), later rows one iteration ahead
+  int base = (blockIdx.x * (blockDim.x >> 5) + warp) * rpw * UNR;
+  uint4 u[UNR][VPL];
+  load_rows(base, u);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // FiLM coefficients of this batch row
+    s_fs[c] = ss ? 1.f + ss[static_cast<size_t>(b) * ss_stride + c] : 1.f;
+    s_ft[c] = ss ? ss[static_cast<size_t>(b) * ss_stride + C + c] : 0.f;
+  }
+  __syncthreads();
+  for (; base < T; base += step) {
+    uint4 unx[UNR][VPL];
+    if (base + step < T) load_rows(base + step, unx);
 #pragma unroll
     for (int un = 0; un < UNR; ++un) {
       const int row = base + un * rpw + sub;
@@ -221,6 +244,10 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
         }
       }
     }
+#pragma unroll
+    for (int un = 0; un < UNR; ++un)
+#pragma unroll
+      for (int it = 0; it < VPL; ++it) u[un][it] = unx[un][it];
   }
   if (do_stats) {
     // lanes l, l+lpr, l+2*lpr, ... hold the same channels: fold them before touching smem
@@ -381,6 +408,7 @@ extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const fl
   ADP_CHECK(C % 8 == 0 && C <= kMaxC && groups > 0 && C % groups == 0,
             "adp_gn_silu: C=%d groups=%d unsupported", C, groups);
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
+  ADP_CHECK(nvec < (1ull << 31), "adp_gn_silu: T*C/8 = %zu does not fit 31 bits", nvec);
   dim3 grid(pick_grid(nvec, 1024, 148 * 16 / (B < 16 ? B : 16) + 1), B);
   ADP_CUDA(launch_k(gn_silu_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
                     static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,

@@ -265,7 +265,8 @@ def main():
     e2e_value = clips * CLIP_SECONDS / (e2e_ms / args.steps * 1e-3)
 
     # ---- roofline of the dominant kernel: instrumented eager pass of the same plan
-    plan = next(p for k, p in net._plans.items() if k[4] == "sample")
+    plan = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
+    cond_plan = next((p for k, p in net._plans.items() if k[0] == "cond"), None)
     table = net.profile_plan(plan, iters=5)
     hbm, tf_burst, tf_sust, which = peaks()
     top = max(table.values(), key=lambda r: r["ms_total"])
@@ -301,7 +302,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "audio-s/s",
                     "h2d_bytes_per_step": host_noise.numel() * 4,
                     "d2h_bytes_per_step": host_out.numel() * 4},
-            "gpu_launches": plan.n_kernels * NUM_STEPS * args.steps,
+            # per step the net's kernels; per sample() call the 6 conditioning launches
+            "gpu_launches": (plan.n_kernels * NUM_STEPS + (6 if cond_plan is not None else 0)) * args.steps,
             "ms_per_net_eval": ms_per_step / NUM_STEPS,
             "roofline": roof}
     if not args.no_train:
