@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         "adp_gn_silu": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "adp_gn_stats": [vp, vp, i32, i32, i32, i32, vp],
         "adp_ln_film": [vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, vp],
+        "adp_ln_film_dual": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, f32, vp],
         "adp_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, vp],
         "adp_skinny_linear": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "adp_time_features": [vp, vp, vp, i32, i32, i32, vp],
@@ -125,7 +126,7 @@ def check(rc: int, what: str) -> None:
 
 
 EXPORTS = ["adp_version", "adp_last_error", "adp_device_check", "adp_conv_gemm", "adp_gn_silu",
-           "adp_gn_stats", "adp_ln_film", "adp_attention", "adp_skinny_linear",
+           "adp_gn_stats", "adp_ln_film", "adp_ln_film_dual", "adp_attention", "adp_skinny_linear",
            "adp_time_features", "adp_stem_in", "adp_stem_out", "adp_narrow_conv",
            "adp_sampler_step", "adp_silu_bf16", "adp_debug_set", "adp_wgrad", "adp_gn_silu_bwd",
            "adp_gn_bwd_apply", "adp_ln_film_bwd", "adp_colsum", "adp_skip_gate",

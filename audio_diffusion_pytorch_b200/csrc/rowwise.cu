@@ -135,7 +135,7 @@ template <int VPL, bool PER_CH, int UNR>
 __global__ void __launch_bounds__(256)
 ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ ss,
                int ss_stride, double* __restrict__ stats, int T, int C, int lpr, int groups,
-               float eps) {
+               float eps, uint4* __restrict__ y2, float eps2) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float s_acc[2 * 64];
@@ -229,6 +229,7 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
           o4[j] = pack_bf16(y0, y1);
           const float2 rr = unpack_bf16(o4[j]);   // statistics of what is stored
           r[2 * j] = rr.x; r[2 * j + 1] = rr.y;
+          v[it][2 * j] = rr.x; v[it][2 * j + 1] = rr.y;   // kept for the second LayerNorm
         }
         if (ok) {
           yb[static_cast<size_t>(row) * vpr + it * lpr + l] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
@@ -240,6 +241,33 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
 #pragma unroll
               for (int j = 0; j < 8; ++j) { as[it] += r[j]; aq[it] += r[j] * r[j]; }
             }
+          }
+        }
+      }
+      if (y2) {   // y2 = LayerNorm(y; eps2) of the stored (rounded) y: the attention pre-norm
+        float sum2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < VPL; ++it)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum2 += v[it][j];
+        for (int o = lpr >> 1; o > 0; o >>= 1) sum2 += __shfl_xor_sync(0xffffffffu, sum2, o);
+        const float mean2 = sum2 * inv_c;
+        float sq2 = 0.f;
+#pragma unroll
+        for (int it = 0; it < VPL; ++it)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = v[it][j] - mean2; sq2 += d * d; }
+        for (int o = lpr >> 1; o > 0; o >>= 1) sq2 += __shfl_xor_sync(0xffffffffu, sq2, o);
+        const float rstd2 = rsqrtf(sq2 * inv_c + eps2);
+        if (ok) {
+#pragma unroll
+          for (int it = 0; it < VPL; ++it) {
+            uint4 o;
+            o.x = pack_bf16((v[it][0] - mean2) * rstd2, (v[it][1] - mean2) * rstd2);
+            o.y = pack_bf16((v[it][2] - mean2) * rstd2, (v[it][3] - mean2) * rstd2);
+            o.z = pack_bf16((v[it][4] - mean2) * rstd2, (v[it][5] - mean2) * rstd2);
+            o.w = pack_bf16((v[it][6] - mean2) * rstd2, (v[it][7] - mean2) * rstd2);
+            y2[static_cast<size_t>(b) * T * vpr + static_cast<size_t>(row) * vpr + it * lpr + l] = o;
           }
         }
       }
@@ -433,6 +461,14 @@ extern "C" int adp_gn_stats(const void* x, double* stats, int32_t B, int32_t T, 
 extern "C" int adp_ln_film(const void* x, void* y, const float* scale_shift, int32_t ss_stride,
                            double* stats_out, int32_t B, int32_t T, int32_t C, int32_t groups,
                            float eps, adp_stream_t stream) {
+  return adp_ln_film_dual(x, y, nullptr, scale_shift, ss_stride, stats_out, B, T, C, groups, eps,
+                          0.f, stream);
+}
+
+extern "C" int adp_ln_film_dual(const void* x, void* y, void* y2, const float* scale_shift,
+                                int32_t ss_stride, double* stats_out, int32_t B, int32_t T,
+                                int32_t C, int32_t groups, float eps, float eps2,
+                                adp_stream_t stream) {
   ADP_CHECK(x && y, "adp_ln_film: null pointer");
   ADP_CHECK(C % 8 == 0, "adp_ln_film: C=%d must be a multiple of 8", C);
   const int vpr = C / 8;
@@ -462,7 +498,7 @@ extern "C" int adp_ln_film(const void* x, void* y, const float* scale_shift, int
 #define ADP_LN(VPL, PC)                                                                         \
   ADP_CUDA(launch_k(ln_film_kernel<VPL, PC, (VPL <= 2 ? 2 : 1)>, grid, dim3(256), (size_t)0, s, \
                     xi, yo, scale_shift, (int)ss_stride, stats_out, (int)T, (int)C, (int)lpr,   \
-                    (int)groups, eps))
+                    (int)groups, eps, static_cast<uint4*>(y2), eps2))
   if (per_ch) ADP_LN(1, true);
   else if (vpl == 1) ADP_LN(1, false);
   else if (vpl == 2) ADP_LN(2, false);

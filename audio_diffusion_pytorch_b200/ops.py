@@ -189,11 +189,19 @@ def gn_stats(x: Tensor, stats: Tensor, groups: int) -> Tensor:
 
 
 def ln_film(x: Tensor, y: Tensor, scale_shift: Optional[Tensor] = None, ss_stride: int = 0,
-            stats_out: Optional[Tensor] = None, groups: int = 8, eps: float = 1e-6) -> Tensor:
+            stats_out: Optional[Tensor] = None, groups: int = 8, eps: float = 1e-6,
+            y2: Optional[Tensor] = None, eps2: float = 1e-5) -> Tensor:
+    """y = LN(x)*(1+scale)+shift; with y2 also y2 = LN(y; eps2) in the same pass."""
     B, T, Cc = x.shape
-    _launch(lambda: _lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
-                                           _p(stats_out), B, T, Cc, groups, eps, _stream()),
-            "adp_ln_film", lambda: (f"ln_film[M={B * T} C={Cc}]", 0, _nb(x, y)))
+    if y2 is None:
+        _launch(lambda: _lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
+                                               _p(stats_out), B, T, Cc, groups, eps, _stream()),
+                "adp_ln_film", lambda: (f"ln_film[M={B * T} C={Cc}]", 0, _nb(x, y)))
+    else:
+        _launch(lambda: _lib.lib().adp_ln_film_dual(x.data_ptr(), y.data_ptr(), y2.data_ptr(),
+                                                    _p(scale_shift), ss_stride, _p(stats_out), B, T, Cc,
+                                                    groups, eps, eps2, _stream()),
+                "adp_ln_film_dual", lambda: (f"ln_film_dual[M={B * T} C={Cc}]", 0, _nb(x, y, y2)))
     return y
 
 

@@ -510,8 +510,10 @@ class B200UNet(nn.Module):
                         plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
                             a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
                         pool.put(a)
-                    plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats: ops.ln_film(
-                        r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS))
+                    xn_first = pool.get(Bh, Tl, C) if (has_att or has_cross) else None
+                    # Modulation and the following attention pre-norm in ONE pass over the rows
+                    plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats, xn=xn_first: ops.ln_film(
+                        r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS, y2=xn, eps2=self.ATT_LN_EPS))
                     pool.put(h)
                     pool.put(r)
                 # the item's input is dead now (a level's skip is the chain's *output*)
@@ -524,10 +526,13 @@ class B200UNet(nn.Module):
                     ap = ip[kind]
                     is_last_att = kind == "cross" or not has_cross
                     out_stats = new_stats() if (want_stats and is_last_att) else None
-                    xn = pool.get(Bh, Tl, C)
                     o = pool.get(Bh, Tl, mid)
                     y2 = pool.get(Bh, Tl, C)
-                    plan.add(lambda x=x, xn=xn: ops.ln_film(x, xn, None, 0, None, G, self.ATT_LN_EPS))
+                    if not narrow and xn_first is not None:
+                        xn, xn_first = xn_first, None      # produced by the fused Modulation pass
+                    else:
+                        xn = pool.get(Bh, Tl, C)
+                        plan.add(lambda x=x, xn=xn: ops.ln_film(x, xn, None, 0, None, G, self.ATT_LN_EPS))
                     if kind == "att":
                         qkv = pool.get(Bh, Tl, 3 * mid)
                         plan.add(lambda xn=xn, qkv=qkv, ap=ap: ops.conv_gemm(

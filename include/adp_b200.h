@@ -101,6 +101,14 @@ int adp_ln_film(const void* x, void* y, const float* scale_shift, int32_t ss_str
                 double* stats_out, int32_t B, int32_t T, int32_t C, int32_t groups, float eps,
                 adp_stream_t stream);
 
+/* adp_ln_film plus, in the same pass, y2 = LayerNorm_C(y; no affine, eps2) of the stored y:
+ * a ModulationItem followed by an AttentionItem (a_unet apex.py block order) needs both the
+ * modulated tensor (the attention's residual) and its pre-norm (input of the q/k/v projection).
+ * y2 == NULL degenerates to adp_ln_film. */
+int adp_ln_film_dual(const void* x, void* y, void* y2, const float* scale_shift,
+                     int32_t ss_stride, double* stats_out, int32_t B, int32_t T, int32_t C,
+                     int32_t groups, float eps, float eps2, adp_stream_t stream);
+
 /* o = softmax(q k^T * scale) v per (batch, head), head dim 64 -- a_unet AttentionBase.
  * q: bf16 [B][Tq][ldq] (head h at columns [h*64,(h+1)*64)), k/v likewise over Tk rows,
  * o: bf16 [B][Tq][ldo].  tcgen05 flash attention (S and O accumulators in TMEM). */

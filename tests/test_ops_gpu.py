@@ -179,6 +179,22 @@ def test_ln_film(ops, B, T, C, film):
     assert_close(stats, stats_of(y, groups), 1e-4, 1e-2, f"ln_film stats C{C}")
 
 
+@pytest.mark.parametrize("B,T,C", [(2, 300, 1024), (2, 257, 512), (1, 1000, 64), (2, 128, 256)])
+def test_ln_film_dual(ops, B, T, C):
+    """Modulation + attention pre-norm in one pass: y2 must equal LayerNorm of the STORED y."""
+    x = bf(rnd(B, T, C, seed=26) * 2.0 + 0.5)
+    ss = rnd(B, 2 * C, seed=27) * 0.3
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=DEV)
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    ops.ln_film(x, y, ss, 2 * C, stats, 8, 1e-6, y2=y2, eps2=1e-5)
+    y_single = torch.empty_like(x)
+    ops.ln_film(x, y_single, ss, 2 * C, None, 8, 1e-6)
+    assert torch.equal(y, y_single), "dual pass changed the first output"
+    ref2 = F.layer_norm(y.float(), (C,), eps=1e-5)
+    assert_close(y2, ref2, 2 ** -7, 1e-2, f"ln_film_dual y2 C{C}")
+    assert_close(stats, stats_of(y, 8), 1e-4, 1e-2, f"ln_film_dual stats C{C}")
+
+
 @pytest.mark.parametrize("B,K,N,in_act,out_act", [(8, 1024, 1024, 0, 1), (3, 264, 1024, 0, 1),
                                                   (20, 1024, 520, 2, 0), (1, 64, 40, 1, 2)])
 def test_skinny_linear(ops, B, K, N, in_act, out_act):
