@@ -189,6 +189,13 @@ def train_step_bench(adp, dev, world, dist, steps, warmup, batch=4):
             "audio_s_per_s": batch * world * CLIP_SECONDS / (float(ms.item()) * 1e-3)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the
+# same shapes (tools/profile_r1c.sh -> profiles/r1_ncu_conv_*_v4.txt); None for other kernels
+NCU_DRAM_BYTES = {"conv_gemm[k3 M=2048 K=1024 N=1024x1]": 14776064.0,
+                  "conv_gemm[k3 M=32768 K=128 N=128x1]": 17011968.0}
+NCU_DRAM_SOURCE = "profiles/r1_ncu_conv_L7_v4.txt, profiles/r1_ncu_conv_L3_v4.txt"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,7 +289,9 @@ def main():
                 "frac": achieved / hbm}
     roof.update({"kernel": top["name"], "launches_per_net_eval": top["count"],
                  "share_of_step": top["ms_total"] / step_ms, "peak_source": which,
-                 "traffic": None, "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"]})
+                 "traffic": NCU_DRAM_BYTES.get(top["name"]), "traffic_source": NCU_DRAM_SOURCE
+                 if top["name"] in NCU_DRAM_BYTES else None,
+                 "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"]})
     # whole-step roofline: sum over levels of max(flop time, byte time)
     t_bound = sum(max(r["flops"] / (tf_sust * 1e12), r["bytes"] / (hbm * 1e9)) * r["count"]
                   for r in table.values())
