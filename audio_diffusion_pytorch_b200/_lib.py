@@ -39,7 +39,7 @@ class NarrowConvArgs(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("stats_in", vp), ("gamma", vp), ("beta", vp), ("w", vp),
                 ("bias", vp), ("residual", vp), ("scale_shift", vp), ("stats_out", vp),
                 ("ss_stride", i32), ("B", i32), ("T", i32), ("C", i32), ("groups", i32),
-                ("gn_eps", f32), ("ln_eps", f32)]
+                ("gn_eps", f32), ("ln_eps", f32), ("w_packed", vp)]
 
 
 class WgradArgs(C.Structure):

@@ -11,23 +11,27 @@ constexpr int kMaxC = 2048;
 
 // --------------------------------------------------------------------------- gn_silu
 // y = silu(x * a[b,c] + d[b,c]),  a = gamma*rstd, d = beta - mean*a  from (sum, sumsq).
-// Each CTA streams tiles of 1024 vectors, four independent 16-byte loads in flight per thread.
+// Each CTA streams tiles of 1024 vectors, four independent 16-byte loads in flight per thread
+// plus the next tile's.  REG: C/8 divides 256, so a thread meets the SAME 8 channels in every
+// vector it touches and keeps their coefficients in registers — the statistics / gamma / beta
+// loads go out together with the first data loads (one latency round, no smem, no barrier; the
+// deep levels' launches are latency-, not bandwidth-bound).  Otherwise coefficients of all C
+// channels are staged in smem.
+template <bool REG>
 __global__ void __launch_bounds__(256)
 gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                const float* __restrict__ gamma, const float* __restrict__ beta, int T, int C,
                int groups, float eps) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ __align__(16) float s_a[kMaxC];
-  __shared__ __align__(16) float s_d[kMaxC];
+  __shared__ __align__(16) float s_a[REG ? 8 : kMaxC];
+  __shared__ __align__(16) float s_d[REG ? 8 : kMaxC];
   const int b = blockIdx.y;
   const int gsz = C / groups;
   const int vpr = C >> 3;  // vectors per row
   const uint32_t nvec = static_cast<uint32_t>(T) * vpr;          // < 2^31 (checked by the host)
   const uint4* xb = x + static_cast<size_t>(b) * nvec;
   uint4* yb = y + static_cast<size_t>(b) * nvec;
-  // first tile's loads go out BEFORE the coefficients are derived from the statistics: the two
-  // global-latency chains of this (latency-bound at the deep levels) kernel overlap
   uint4 u[4];
   uint32_t base = blockIdx.x * 1024u;
 #pragma unroll
@@ -36,17 +40,49 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
     u[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
   }
   const double inv_n = 1.0 / (static_cast<double>(gsz) * T);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gsz;
-    const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
-    const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
-    const double mean = s * inv_n;                      // fp64 only where cancellation bites
-    const float var = fmaxf(static_cast<float>(q * inv_n - mean * mean), 0.f);
-    const float a = gamma[c] * rsqrtf(var + eps);
-    s_a[c] = a;
-    s_d[c] = beta[c] - static_cast<float>(mean) * a;
+  float ca[8], cd[8];
+  if constexpr (REG) {
+    const int c0 = (threadIdx.x & (vpr - 1)) << 3;      // vpr is a power of two dividing 256
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    if (gsz >= 8) {            // the 8 channels share one group
+      const int g = c0 / gsz;
+      const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
+      const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
+      const double mean = s * inv_n;                    // fp64 only where cancellation bites
+      const float var = fmaxf(static_cast<float>(q * inv_n - mean * mean), 0.f);
+      const float rstd = rsqrtf(var + eps), fm = static_cast<float>(mean);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ca[j] = gm[j] * rstd; cd[j] = bt[j] - fm * ca[j]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / gsz;
+        const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
+        const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
+        const double mean = s * inv_n;
+        const float var = fmaxf(static_cast<float>(q * inv_n - mean * mean), 0.f);
+        ca[j] = gm[j] * rsqrtf(var + eps);
+        cd[j] = bt[j] - static_cast<float>(mean) * ca[j];
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / gsz;
+      const double s = stats[(static_cast<size_t>(b) * groups + g) * 2];
+      const double q = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1];
+      const double mean = s * inv_n;
+      const float var = fmaxf(static_cast<float>(q * inv_n - mean * mean), 0.f);
+      const float a = gamma[c] * rsqrtf(var + eps);
+      s_a[c] = a;
+      s_d[c] = beta[c] - static_cast<float>(mean) * a;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (; base < nvec; base += gridDim.x * 1024u) {
     const uint32_t nbase = base + gridDim.x * 1024u;
     uint4 un[4];
@@ -61,18 +97,18 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
     for (int k = 0; k < 4; ++k) {
       const uint32_t i = base + k * 256 + threadIdx.x;
       if (i >= nvec) continue;
-      const int c = static_cast<int>(i % static_cast<uint32_t>(vpr)) << 3;
-      const float4 a0 = *reinterpret_cast<const float4*>(&s_a[c]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&s_a[c + 4]);
-      const float4 d0 = *reinterpret_cast<const float4*>(&s_d[c]);
-      const float4 d1 = *reinterpret_cast<const float4*>(&s_d[c + 4]);
+      if constexpr (!REG) {
+        const int c = static_cast<int>(i % static_cast<uint32_t>(vpr)) << 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[j] = s_a[c + j]; cd[j] = s_d[c + j]; }
+      }
       const float2 f0 = unpack_bf16(u[k].x), f1 = unpack_bf16(u[k].y);
       const float2 f2 = unpack_bf16(u[k].z), f3 = unpack_bf16(u[k].w);
       uint4 o;
-      o.x = pack_bf16(silu_f(f0.x * a0.x + d0.x), silu_f(f0.y * a0.y + d0.y));
-      o.y = pack_bf16(silu_f(f1.x * a0.z + d0.z), silu_f(f1.y * a0.w + d0.w));
-      o.z = pack_bf16(silu_f(f2.x * a1.x + d1.x), silu_f(f2.y * a1.y + d1.y));
-      o.w = pack_bf16(silu_f(f3.x * a1.z + d1.z), silu_f(f3.y * a1.w + d1.w));
+      o.x = pack_bf16(silu_f(f0.x * ca[0] + cd[0]), silu_f(f0.y * ca[1] + cd[1]));
+      o.y = pack_bf16(silu_f(f1.x * ca[2] + cd[2]), silu_f(f1.y * ca[3] + cd[3]));
+      o.z = pack_bf16(silu_f(f2.x * ca[4] + cd[4]), silu_f(f2.y * ca[5] + cd[5]));
+      o.w = pack_bf16(silu_f(f3.x * ca[6] + cd[6]), silu_f(f3.y * ca[7] + cd[7]));
       yb[i] = o;
     }
 #pragma unroll
@@ -438,9 +474,16 @@ extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const fl
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
   ADP_CHECK(nvec < (1ull << 31), "adp_gn_silu: T*C/8 = %zu does not fit 31 bits", nvec);
   dim3 grid(pick_grid(nvec, 1024, 148 * 16 / (B < 16 ? B : 16) + 1), B);
-  ADP_CUDA(launch_k(gn_silu_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
-                    static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
-                    (int)T, (int)C, (int)groups, eps));
+  const int vpr = C / 8;
+  if (vpr <= 256 && (vpr & (vpr - 1)) == 0) {
+    ADP_CUDA(launch_k(gn_silu_kernel<true>, grid, dim3(256), (size_t)0, as_stream(stream),
+                      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
+                      (int)T, (int)C, (int)groups, eps));
+  } else {
+    ADP_CUDA(launch_k(gn_silu_kernel<false>, grid, dim3(256), (size_t)0, as_stream(stream),
+                      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
+                      (int)T, (int)C, (int)groups, eps));
+  }
   ADP_LAUNCH_CHECK();
   return 0;
 }

@@ -498,6 +498,8 @@ __global__ void __launch_bounds__(256) narrow_conv_kernel(const adp_narrow_conv_
   }
 }
 
+int mid_conv(const adp_narrow_conv_args& a, cudaStream_t stream);   // mid_conv.cu
+
 }  // namespace adp
 
 using namespace adp;
@@ -547,9 +549,15 @@ extern "C" int adp_narrow_conv(const adp_narrow_conv_args* args, adp_stream_t st
   ADP_CHECK(args && args->x && args->y && args->stats_in && args->gamma && args->beta && args->w,
             "adp_narrow_conv: null pointer");
   const adp_narrow_conv_args& a = *args;
-  ADP_CHECK(a.C == 8, "adp_narrow_conv: only C == 8 is built (C=%d); wider levels use adp_conv_gemm",
-            a.C);
-  ADP_CHECK(a.groups > 0 && a.C % a.groups == 0, "adp_narrow_conv: groups=%d", a.groups);
+  ADP_CHECK(a.C == 8 || a.C == 32 || a.C == 64,
+            "adp_narrow_conv: C=%d is not built (8, 32, 64); wider levels use adp_conv_gemm", a.C);
+  ADP_CHECK(a.groups > 0 && a.C % a.groups == 0 && a.groups <= 64, "adp_narrow_conv: groups=%d", a.groups);
+  if (a.C != 8) {
+    ADP_CHECK((a.C / a.groups) % 2 == 0, "adp_narrow_conv: group size %d must be even", a.C / a.groups);
+    if (int e = mid_conv(a, as_stream(stream))) return e;
+    ADP_LAUNCH_CHECK();
+    return 0;
+  }
   // persistent blocks: one wave of resident blocks shares the tiles of each batch element
   dim3 grid(persistent_gx(narrow_conv_kernel<8>, 256, 0, a.B, (a.T + 255) / 256), a.B);
   ADP_CUDA(launch_k(narrow_conv_kernel<8>, grid, dim3(256), (size_t)0, as_stream(stream), a));

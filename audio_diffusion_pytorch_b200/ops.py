@@ -286,8 +286,9 @@ def narrow_conv(x: Tensor, y: Tensor, stats_in: Tensor, gamma: Tensor, beta: Ten
                 bias: Optional[Tensor], groups: int, *, residual: Optional[Tensor] = None,
                 scale_shift: Optional[Tensor] = None, ss_stride: int = 0,
                 stats_out: Optional[Tensor] = None, gn_eps: float = 1e-5,
-                ln_eps: float = 1e-6) -> Tensor:
+                ln_eps: float = 1e-6, w_packed: Optional[Tensor] = None) -> Tensor:
     a = NarrowConvArgs()
+    a.w_packed = _p(w_packed)
     a.x, a.y, a.stats_in = x.data_ptr(), y.data_ptr(), stats_in.data_ptr()
     a.gamma, a.beta, a.w, a.bias = gamma.data_ptr(), beta.data_ptr(), w.data_ptr(), _p(bias)
     a.residual, a.scale_shift, a.stats_out = _p(residual), _p(scale_shift), _p(stats_out)
@@ -298,7 +299,14 @@ def narrow_conv(x: Tensor, y: Tensor, stats_in: Tensor, gamma: Tensor, beta: Ten
             lambda: (f"narrow_conv[M={x.shape[0] * x.shape[1]} C={x.shape[2]}"
                      f"{' +res+film' if residual is not None else ''}]",
                      2.0 * x.numel() * 3 * x.shape[2], _nb(x, y, residual)))
-    return y
+    return y   # C in (8, 32, 64): stem.cu narrow_conv_kernel / mid_conv.cu
+
+
+def pack_mid_conv(w: Tensor) -> Tensor:
+    """conv weight [C][C][3] (C = 32 / 64) -> bf16 [C][3*C], k = tap*C + ci: the smem image of
+    adp_narrow_conv's B operand (adp_narrow_conv_args.w_packed)."""
+    co, ci, k = w.shape
+    return w.detach().permute(0, 2, 1).reshape(co, k * ci).to(torch.bfloat16).contiguous()
 
 
 def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:

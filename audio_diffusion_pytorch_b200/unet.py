@@ -234,6 +234,9 @@ class B200UNet(nn.Module):
         # config (6.85 vs 6.0 ms / evaluation, profiles/r1_gn_fusion.txt): every N tile repeats
         # the transform of its A rows, so it only pays for N <= BN.  Off by default.
         self.fuse_groupnorm = False
+        # C = 32 / 64 ConvBlocks as ONE fused kernel (GroupNorm+SiLU -> conv3 -> +res -> LN/FiLM ->
+        # statistics, csrc/mid_conv.cu) instead of three: those levels are HBM-bound
+        self.fuse_thin_levels = True
 
     # ------------------------------------------------------------------ weights
     def levels(self) -> List[LevelParams]:
@@ -318,6 +321,9 @@ class B200UNet(nn.Module):
                 d["w1"], d["w2"] = f32(r.conv1.weight), f32(r.conv2.weight)
             else:
                 d["w1"], d["w2"] = ops.pack_conv(r.conv1.weight.detach()), ops.pack_conv(r.conv2.weight.detach())
+                if r.conv1.weight.shape[0] in (32, 64):    # thin levels: fused ConvBlock kernel
+                    d["w1_raw"], d["w2_raw"] = f32(r.conv1.weight), f32(r.conv2.weight)
+                    d["w1_mid"], d["w2_mid"] = ops.pack_mid_conv(r.conv1.weight), ops.pack_mid_conv(r.conv2.weight)
             if it.attention is not None:
                 d["att"] = pack_att(it.attention, True)
             if it.cross is not None:
@@ -468,6 +474,9 @@ class B200UNet(nn.Module):
                       last_needs_stats: bool) -> Tuple[Tensor, Optional[Tensor]]:
             C = lv.ch
             narrow = C == 8
+            # thin levels (C = 32, 64) are HBM-bound: one fused ConvBlock kernel (mid_conv.cu)
+            # instead of gn_silu -> conv_gemm (-> ln_film)
+            thin = narrow or (self.fuse_thin_levels and C in (32, 64))
             for idx, ip in enumerate(items_p):
                 ss = ss_all[:, ip["ss_off"]:]
                 has_att, has_cross = "att" in ip, "cross" in ip
@@ -475,16 +484,18 @@ class B200UNet(nn.Module):
                 want_stats = (not item_last) or last_needs_stats
                 mod_stats = new_stats() if (want_stats and not (has_att or has_cross)) else None
                 h_stats = new_stats()
-                if narrow:
+                if thin:
                     h = pool.get(Bh, Tl, C)
                     y = pool.get(Bh, Tl, C)
-                    plan.add(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.narrow_conv(
-                        x, h, s, ip["gn1"][0], ip["gn1"][1], ip["w1"], ip["b1"], G, stats_out=hs,
-                        gn_eps=self.GN_EPS))
-                    plan.add(lambda x=x, h=h, y=y, hs=h_stats, ms=mod_stats, ip=ip, ss=ss: ops.narrow_conv(
-                        h, y, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], ip["b2"], G, residual=x,
-                        scale_shift=ss, ss_stride=ss_stride, stats_out=ms, gn_eps=self.GN_EPS,
-                        ln_eps=self.MOD_LN_EPS))
+                    w1, w2 = (ip["w1"], ip["w2"]) if narrow else (ip["w1_raw"], ip["w2_raw"])
+                    p1, p2 = (None, None) if narrow else (ip["w1_mid"], ip["w2_mid"])
+                    plan.add(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip, w1=w1, p1=p1: ops.narrow_conv(
+                        x, h, s, ip["gn1"][0], ip["gn1"][1], w1, ip["b1"], G, stats_out=hs,
+                        gn_eps=self.GN_EPS, w_packed=p1))
+                    plan.add(lambda x=x, h=h, y=y, hs=h_stats, ms=mod_stats, ip=ip, ss=ss, w2=w2, p2=p2:
+                             ops.narrow_conv(h, y, hs, ip["gn2"][0], ip["gn2"][1], w2, ip["b2"], G,
+                                             residual=x, scale_shift=ss, ss_stride=ss_stride, stats_out=ms,
+                                             gn_eps=self.GN_EPS, ln_eps=self.MOD_LN_EPS, w_packed=p2))
                     pool.put(h)
                 else:
                     h = pool.get(Bh, Tl, C)
@@ -528,7 +539,7 @@ class B200UNet(nn.Module):
                     out_stats = new_stats() if (want_stats and is_last_att) else None
                     o = pool.get(Bh, Tl, mid)
                     y2 = pool.get(Bh, Tl, C)
-                    if not narrow and xn_first is not None:
+                    if not thin and xn_first is not None:
                         xn, xn_first = xn_first, None      # produced by the fused Modulation pass
                     else:
                         xn = pool.get(Bh, Tl, C)

@@ -190,7 +190,7 @@ int adp_stem_out(const adp_stem_out_args* args, adp_stream_t stream);
  * and the GroupNorm statistics of what is written.  (a_unet ConvBlock / ResnetBlock /
  * Modulation; wide levels use adp_gn_silu + adp_conv_gemm + adp_ln_film.) */
 typedef struct adp_narrow_conv_args {
-  const void* x;            /* bf16 [B][T][C]                        */
+  const void* x;            /* bf16 [B][T][C], C in {8, 32, 64}      */
   void* y;                  /* bf16 [B][T][C]                        */
   const double* stats_in;   /* fp64 [B][groups][2]                   */
   const float* gamma;       /* fp32 [C]                              */
@@ -203,6 +203,9 @@ typedef struct adp_narrow_conv_args {
   int32_t ss_stride;
   int32_t B, T, C, groups;
   float gn_eps, ln_eps;
+  const void* w_packed;     /* optional, C = 32 / 64 only: the same weights as bf16
+                               [C][3*C] with k = tap*C + ci (saves every block the fp32 ->
+                               bf16 re-layout of w); NULL = convert from w               */
 } adp_narrow_conv_args;
 int adp_narrow_conv(const adp_narrow_conv_args* args, adp_stream_t stream);
 

@@ -148,7 +148,7 @@ def test_conv_gemm_upsample(ops, B, T, ci, co, f):
 
 # -------------------------------------------------------------------------- row-wise
 @pytest.mark.parametrize("B,T,C", [(2, 1000, 8), (2, 512, 32), (2, 300, 64), (1, 256, 512),
-                                   (2, 128, 1024)])
+                                   (2, 128, 1024), (2, 100, 192)])
 def test_gn_silu_and_stats(ops, B, T, C):
     x = bf(rnd(B, T, C, seed=16) * 1.5 + 0.3)
     gamma, beta = rnd(C, seed=17) * 0.2 + 1.0, rnd(C, seed=18) * 0.2
@@ -312,9 +312,10 @@ def test_stem_out(ops, cx, ca, co, c0, f, mode):
         assert_close(dv, 2 * (ref_v - vt[:, :co]) / ref_v.numel(), 1e-3, 1e-8, "dv")
 
 
-@pytest.mark.parametrize("film,res", [(False, False), (True, True)])
-def test_narrow_conv(ops, film, res):
-    B, T, C, groups = 2, 3000, 8, 8
+@pytest.mark.parametrize("C", [8, 32, 64])
+@pytest.mark.parametrize("film,res", [(False, False), (True, True), (False, True)])
+def test_narrow_conv(ops, film, res, C):
+    B, T, groups = 2, 3000, 8
     x = bf(rnd(B, T, C, seed=41) * 1.3 + 0.2)
     stats_in = stats_of(x, groups).contiguous()
     gamma, beta = rnd(C, seed=42) * 0.2 + 1.0, rnd(C, seed=43) * 0.2
@@ -326,6 +327,11 @@ def test_narrow_conv(ops, film, res):
     y = torch.empty_like(x)
     ops.narrow_conv(x, y, stats_in, gamma, beta, w, bias, groups, residual=resid, scale_shift=ss,
                     ss_stride=2 * C, stats_out=stats_out)
+    if C != 8:      # host-packed bf16 weights must give the identical result
+        y_p = torch.empty_like(x)
+        ops.narrow_conv(x, y_p, stats_in, gamma, beta, w, bias, groups, residual=resid, scale_shift=ss,
+                        ss_stride=2 * C, w_packed=ops.pack_mid_conv(w))
+        assert torch.equal(y, y_p), "w_packed path differs from the fp32-weight path"
     a = F.silu(F.group_norm(x.float().transpose(1, 2), groups, gamma, beta, 1e-5))
     ref = F.conv1d(a, w, bias, padding=1).transpose(1, 2)
     if res:

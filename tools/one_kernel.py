@@ -1,5 +1,5 @@
 """Launches one kernel shape repeatedly (for `ncu --set full`).
-usage: python tools/one_kernel.py conv M K N taps [block_n [stats]] | attn B H T | lnfilm B T C | gnsilu B T C"""
+usage: python tools/one_kernel.py conv M K N taps [block_n [stats]] | attn B H T | lnfilm B T C | gnsilu B T C | mid B T C"""
 import os
 import sys
 
@@ -51,5 +51,20 @@ elif kind == "gnsilu":
     g, bb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     for _ in range(reps):
         ops.gn_silu(x, y, st, g, bb, 8, 1e-5)
+elif kind == "mid":
+    B, T, C = a
+    x = torch.randn(B, T, C, device=dev).bfloat16()
+    y = torch.empty_like(x)
+    res = torch.randn_like(x)
+    st = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64)
+    ops.gn_stats(x, st, 8)
+    so = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64)
+    g, bb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+    w = torch.randn(C, C, 3, device=dev) * (3 * C) ** -0.5
+    bias = torch.randn(C, device=dev)
+    ss = torch.randn(B, 2 * C, device=dev) * 0.3
+    for _ in range(reps):
+        ops.narrow_conv(x, y, st, g, bb, w, bias, 8, residual=res, scale_shift=ss, ss_stride=2 * C,
+                        stats_out=so)
 torch.cuda.synchronize()
 print("done")

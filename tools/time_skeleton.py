@@ -8,7 +8,8 @@ from audio_diffusion_pytorch_b200 import _lib
 from tools.time_gemm import run  # noqa
 
 L = _lib.lib()
-shapes = [("L7 conv3", 2048, 1024, 1024, 3, 128), ("L8 conv3", 1024, 1024, 1024, 3, 64),
+shapes = [("L1 conv3", 524288, 32, 32, 3, 32), ("L2 conv3", 131072, 64, 64, 3, 64),
+          ("L7 conv3", 2048, 1024, 1024, 3, 128), ("L8 conv3", 1024, 1024, 1024, 3, 64),
           ("L5 conv3", 8192, 512, 512, 3, 128), ("L7 qkv", 2048, 1024, 1536, 1, 128),
           ("L7 k1 1024", 2048, 1024, 1024, 1, 128), ("L3 conv3", 32768, 128, 128, 3, 128)]
 modes = [("full", 0), ("noMMA", 1), ("noLOAD", 2), ("neither", 3), ("neither+nodrain", 7), ("floor", 8)]
