@@ -26,7 +26,8 @@ namespace adp {
 
 int conv_gemm_v1(const adp_conv_gemm_args* args, adp_stream_t stream);
 
-// A/B + diagnostic switches (adp_debug_set): [0] impl 2=persistent 1=v1; [3] CTAs/SM override;
+// A/B + diagnostic switches (adp_debug_set): [0] impl 2=persistent 1=v1; [2] 1 = weights are not
+// written by the preceding kernels (fetch them before griddepcontrol.wait); [3] CTAs/SM override;
 // [4] bit0 skip MMAs, bit1 skip TMA loads, bit2 skip drain, bit3 exit at entry (timing
 // experiments only); [5] KC override; [6] PDL; [7] 1 = never use the 8-epilogue-warp variant
 int g_debug[8] = {2, 1, 0, 0, 0, 0, 0, 0};
@@ -53,6 +54,7 @@ struct Gemm2Params {
   int n_stages;          // ring depth
   int a_sub_bytes, w_sub_bytes, stage_bytes, max_taps;
   int dbg;
+  int early_w;           // weights may be fetched before griddepcontrol.wait
   // optional GroupNorm-apply + SiLU on the A operand (transform warps rewrite the smem tile)
   const double* gn_stats;   // fp64 [B][gn_groups][2] of the A tensor
   const float* gn_gamma;
@@ -182,28 +184,57 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform for ptxas
-  pdl_wait();   // inputs (activations, statistics, conditioning) come from the previous kernel
-
+  // Programmatic dependent launch: this kernel may have started while its predecessor still
+  // runs.  Activations / statistics / conditioning come from the predecessor, so every role
+  // that reads them calls griddepcontrol.wait first.  The WEIGHTS do not (p.early_w, set by the
+  // host only while it captures an inference graph): the producer puts the weight boxes of the
+  // first ring stages in flight BEFORE waiting, taking the first-load latency off the
+  // critical path of the many short GEMMs that follow an elementwise kernel.
   if (warp == 0) {
     // ---------------------------------------------------------------------- TMA producer
     {
-      int s = 0;
-      uint32_t ph = 0;
       const uint32_t a_bytes = static_cast<uint32_t>(p.a_rows) * SW;
+      const int total_it = (tile_end - tile_begin) * p.k_stages;
+      int early = 0;
+      if (p.early_w && !(p.dbg & 2)) {
+        early = total_it < p.n_stages ? total_it : p.n_stages;
+        if (elect_one()) {
+          int tile = tile_begin, ks = 0;
+          for (int it = 0; it < early; ++it) {          // stage `it` of the (still empty) ring
+            const TileInfo ti = tile_info(p, tile, BN);
+            uint8_t* st = ring + it * p.stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[it],
+                                  static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes));
+            for (int c = 0; c < p.kc; ++c) {
+              const int k0 = (ks * p.kc + c) * BK;
+              uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
+              for (int tap = 0; tap < ti.ntaps; ++tap)
+                tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[it], tap * p.c_in + k0, ti.n0);
+            }
+            if (++ks == p.k_stages) { ks = 0; ++tile; }
+          }
+        }
+        __syncwarp();
+      }
+      pdl_wait();
+      int s = 0, it = 0;
+      uint32_t ph = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const TileInfo ti = tile_info(p, tile, BN);
         const uint32_t tx = static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes);
-        for (int ks = 0; ks < p.k_stages; ++ks) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+        for (int ks = 0; ks < p.k_stages; ++ks, ++it) {
+          const bool armed = it < early;                 // barrier armed + weights already issued
+          if (!armed) mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = ring + s * p.stage_bytes;
           if (elect_one()) {
             if (p.dbg & 2) {
               mbar_arrive(&full_bar[s]);
             } else {
-              mbar_arrive_expect_tx(&full_bar[s], tx);
+              if (!armed) mbar_arrive_expect_tx(&full_bar[s], tx);
               for (int c = 0; c < p.kc; ++c) {
                 const int k0 = (ks * p.kc + c) * BK;
                 tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
+                if (armed) continue;
                 uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
                 for (int tap = 0; tap < ti.ntaps; ++tap)
                   tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
@@ -264,6 +295,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp < 2 + EW) {
     // -------------------------------------------------------------------------- epilogue
+    pdl_wait();
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -478,6 +510,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------- transform: a = silu(x*ga + de) in place
     // 256 threads, two per tile row.  The TMA tile is SW-byte rows with the 16-byte chunks
     // XOR-swizzled by address bits [7, 7+log2(SW/16)); zero rows (conv padding) stay zero.
+    pdl_wait();
     const int tt = threadIdx.x - (64 + NET);
     constexpr int CPR = SW / 16;                 // 16-byte chunks per row
     constexpr int CPT = CPR / 2 > 0 ? CPR / 2 : 1;   // chunks per thread
@@ -667,6 +700,7 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
   p.total_tiles = a.B * tiles_per_batch * p.n_tiles_n;
   p.a_rows = a_rows;
   p.dbg = g_debug[4];
+  p.early_w = g_debug[2];
   p.gn_stats = a.gn_stats;
   p.gn_gamma = a.gn_gamma;
   p.gn_beta = a.gn_beta;

@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
-from . import ops
+from . import _lib, ops
 
 
 def exists(v) -> bool:
@@ -673,8 +673,14 @@ class B200UNet(nn.Module):
         else:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                plan.run_eager()
+            # inside the captured graph no kernel writes the packed weights, so the GEMMs may
+            # fetch them before their programmatic-dependency wait (conv_gemm.cu, early_w)
+            _lib.lib().adp_debug_set(2, 1)
+            try:
+                with torch.cuda.graph(g):
+                    plan.run_eager()
+            finally:
+                _lib.lib().adp_debug_set(2, 0)
             plan.graph = g
             g.replay()
         plan.runs += 1

@@ -109,6 +109,31 @@ def test_conv_gemm_conv3(ops, B, T, C, co):
     assert_close(stats, ref_stats, 1e-4, 1e-2, f"conv3 stats C{C}")
 
 
+@pytest.mark.parametrize("B,T,C,co", [(2, 512, 64, 64), (1, 256, 1024, 1024), (8, 4096, 32, 32),
+                                      (2, 300, 512, 128)])
+def test_conv_gemm_early_weight_prefetch(ops, B, T, C, co):
+    """adp_debug_set(2, 1): weight boxes of the first ring stages are issued before
+    griddepcontrol.wait (graph-capture mode of the inference plans).  Same bits expected."""
+    from audio_diffusion_pytorch_b200 import _lib
+    x = bf(rnd(B, T, C, seed=4))
+    w = bf(rnd(co, C, 3, scale=(3 * C) ** -0.5, seed=5))
+    bias = rnd(co, seed=6)
+    wp = ops.pack_conv(w)
+    outs = []
+    for flag in (0, 1):
+        _lib.lib().adp_debug_set(2, flag)
+        try:
+            out = torch.empty(B, T, co, dtype=torch.bfloat16, device=DEV)
+            for _ in range(3):      # back-to-back launches: the early fetch overlaps a predecessor
+                ops.conv_gemm(x, wp, out, c_in=C, n_valid=co, taps=(-1, 0, 1), bias=bias)
+            outs.append(out)
+        finally:
+            _lib.lib().adp_debug_set(2, 0)
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=1).transpose(1, 2)
+    assert_close(outs[1], ref, 2 ** -7, 1e-2, f"early-W conv3 C{C}")
+
+
 @pytest.mark.parametrize("B,T,ci,co,f", [(2, 1024, 8, 32, 4), (2, 512, 32, 64, 4),
                                          (1, 256, 128, 256, 2), (2, 96, 64, 128, 2)])
 def test_conv_gemm_downsample(ops, B, T, ci, co, f):
