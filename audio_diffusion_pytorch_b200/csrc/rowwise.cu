@@ -17,7 +17,7 @@ constexpr int kMaxC = 2048;
 // loads go out together with the first data loads (one latency round, no smem, no barrier; the
 // deep levels' launches are latency-, not bandwidth-bound).  Otherwise coefficients of all C
 // channels are staged in smem.
-template <bool REG>
+template <bool REG, int NV>      // NV = 16-byte vectors per thread per tile (1 for small tensors)
 __global__ void __launch_bounds__(256)
 gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                const float* __restrict__ gamma, const float* __restrict__ beta, int T, int C,
@@ -32,10 +32,11 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
   const uint32_t nvec = static_cast<uint32_t>(T) * vpr;          // < 2^31 (checked by the host)
   const uint4* xb = x + static_cast<size_t>(b) * nvec;
   uint4* yb = y + static_cast<size_t>(b) * nvec;
-  uint4 u[4];
-  uint32_t base = blockIdx.x * 1024u;
+  constexpr uint32_t TILE = 256u * NV;
+  uint4 u[NV];
+  uint32_t base = blockIdx.x * TILE;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const uint32_t i = base + k * 256 + threadIdx.x;
     u[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
   }
@@ -83,18 +84,18 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
     }
     __syncthreads();
   }
-  for (; base < nvec; base += gridDim.x * 1024u) {
-    const uint32_t nbase = base + gridDim.x * 1024u;
-    uint4 un[4];
+  for (; base < nvec; base += gridDim.x * TILE) {
+    const uint32_t nbase = base + gridDim.x * TILE;
+    uint4 un[NV];
     if (nbase < nvec) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NV; ++k) {
         const uint32_t i = nbase + k * 256 + threadIdx.x;
         un[k] = i < nvec ? __ldg(xb + i) : make_uint4(0, 0, 0, 0);
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const uint32_t i = base + k * 256 + threadIdx.x;
       if (i >= nvec) continue;
       if constexpr (!REG) {
@@ -112,7 +113,7 @@ gn_silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double*
       yb[i] = o;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = un[k];
+    for (int k = 0; k < NV; ++k) u[k] = un[k];
   }
 }
 
@@ -134,7 +135,7 @@ gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int T, 
   // make the per-thread stride a multiple of vpr so its channels never change
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-  const size_t stride = (nthreads + vpr - 1) / vpr * vpr;
+  const size_t stride = nthreads / vpr * vpr;      // round DOWN: threads >= stride sit out (host: vpr <= 256)
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
@@ -473,17 +474,21 @@ extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const fl
             "adp_gn_silu: C=%d groups=%d unsupported", C, groups);
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
   ADP_CHECK(nvec < (1ull << 31), "adp_gn_silu: T*C/8 = %zu does not fit 31 bits", nvec);
-  dim3 grid(pick_grid(nvec, 1024, 148 * 16 / (B < 16 ? B : 16) + 1), B);
   const int vpr = C / 8;
-  if (vpr <= 256 && (vpr & (vpr - 1)) == 0) {
-    ADP_CUDA(launch_k(gn_silu_kernel<true>, grid, dim3(256), (size_t)0, as_stream(stream),
-                      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
-                      (int)T, (int)C, (int)groups, eps));
-  } else {
-    ADP_CUDA(launch_k(gn_silu_kernel<false>, grid, dim3(256), (size_t)0, as_stream(stream),
-                      static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,
-                      (int)T, (int)C, (int)groups, eps));
-  }
+  const bool reg = vpr <= 256 && (vpr & (vpr - 1)) == 0;
+  // small tensors (the deep levels) are latency-bound: one vector per thread, many blocks
+  const bool small = static_cast<size_t>(B) * nvec <= static_cast<size_t>(148) * 2048 * 2;
+  const int tile = small ? 256 : 1024;
+  dim3 grid(pick_grid(nvec, tile, 148 * 16 / (B < 16 ? B : 16) + 1), B);
+#define ADP_GN(REG, NV)                                                                         \
+  ADP_CUDA(launch_k(gn_silu_kernel<REG, NV>, grid, dim3(256), (size_t)0, as_stream(stream),     \
+                    static_cast<const uint4*>(x), static_cast<uint4*>(y), stats, gamma, beta,    \
+                    (int)T, (int)C, (int)groups, eps))
+  if (reg && small) ADP_GN(true, 1);
+  else if (reg) ADP_GN(true, 4);
+  else if (small) ADP_GN(false, 1);
+  else ADP_GN(false, 4);
+#undef ADP_GN
   ADP_LAUNCH_CHECK();
   return 0;
 }
@@ -491,7 +496,7 @@ extern "C" int adp_gn_silu(const void* x, void* y, const double* stats, const fl
 extern "C" int adp_gn_stats(const void* x, double* stats, int32_t B, int32_t T, int32_t C,
                             int32_t groups, adp_stream_t stream) {
   ADP_CHECK(x && stats, "adp_gn_stats: null pointer");
-  ADP_CHECK(C % 8 == 0 && groups > 0 && groups <= 64 && C % groups == 0,
+  ADP_CHECK(C % 8 == 0 && C <= 2048 && groups > 0 && groups <= 64 && C % groups == 0,
             "adp_gn_stats: C=%d groups=%d unsupported", C, groups);
   const size_t nvec = static_cast<size_t>(T) * (C / 8);
   dim3 grid(pick_grid(nvec, 256 * 8, 148 * 8 / (B < 8 ? B : 8) + 1), B);
@@ -534,7 +539,9 @@ extern "C" int adp_ln_film_dual(const void* x, void* y, void* y2, const float* s
   ADP_CHECK(C <= kMaxLnC, "adp_ln_film: C=%d > %d", C, kMaxLnC);
   const int unr = vpl <= 2 ? 2 : 1;
   const int rows_per_block = 8 * (32 / lpr) * unr;
-  dim3 grid(pick_grid(T, rows_per_block * 2, 148 * 16 / (B < 16 ? B : 16) + 1), B);
+  // deep levels have few rows: one pass per warp (all SMs busy) instead of two
+  const bool few = static_cast<size_t>(B) * ((T + rows_per_block - 1) / rows_per_block) <= 148 * 4;
+  dim3 grid(pick_grid(T, few ? rows_per_block : rows_per_block * 2, 148 * 16 / (B < 16 ? B : 16) + 1), B);
   const uint4* xi = static_cast<const uint4*>(x);
   uint4* yo = static_cast<uint4*>(y);
   cudaStream_t s = as_stream(stream);

@@ -167,7 +167,7 @@ __device__ __forceinline__ void stem_out_conv(const __nv_bfloat16* __restrict__ 
   for (int k = 0; k < 3; ++k) {
     const int idx = t + k - 1;
     if (idx < 0 || idx >= T) continue;       // zero padding of the upsampled signal
-    const int q = idx / f;                   // nearest-neighbour source row
+    const int q = f == 1 ? idx : idx / f;    // nearest-neighbour source row
     (void)Tl;
     const uint4* row = reinterpret_cast<const uint4*>(hb + static_cast<size_t>(q) * c0);
     for (int c8 = 0; c8 < c0; c8 += 8) {
@@ -182,9 +182,11 @@ __device__ __forceinline__ void stem_out_conv(const __nv_bfloat16* __restrict__ 
 #pragma unroll
       for (int o = 0; o < kStemMaxCo; ++o) {
         if (o < co_n) {
-          const float* wp = s_w + (o * 3 + k) * c0 + c8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) y[o] += hv[j] * wp[j];
+          // two 16-byte broadcast reads (c0 % 8 == 0 keeps them aligned) instead of eight scalar
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + (o * 3 + k) * c0 + c8);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_w + (o * 3 + k) * c0 + c8 + 4);
+          y[o] += (hv[0] * w0.x + hv[1] * w0.y) + (hv[2] * w0.z + hv[3] * w0.w) +
+                  (hv[4] * w1.x + hv[5] * w1.y) + (hv[6] * w1.z + hv[7] * w1.w);
         }
       }
     }
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256, 3) stem_out_kernel(const adp_stem_out_arg
   pdl_launch_dependents();
   pdl_wait();
   const int ldg = a.ld_gate > 0 ? a.ld_gate : a.co;
-  extern __shared__ float s_w[];   // conv w [co][3][c0], bias[co], adapt w [co][cin], adapt b[co]
+  extern __shared__ __align__(16) float s_w[];   // conv w [co][3][c0], bias[co], adapt w [co][cin], adapt b[co]
   __shared__ double s_loss[8];
   const int cin = a.cx + a.ca;
   float* s_b = s_w + a.co * 3 * a.c0;
