@@ -102,28 +102,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(steps: int, warmup: int, batch: int = 2):
+def cpu_reference_run(steps: int, warmup: int, budget_s: float = 150.0, batch: int = 1):
     """The reference's own eager CPU path (oracle port over the a_unet shim), fp32, all host
-    threads.  One timed unit = ONE VSampler step at `batch` clips; per-step cost does not
-    depend on the step index (reference diffusion.py:183-188), so a 50-step sample costs 50x."""
+    threads.  One timed unit = ONE VSampler step (reference diffusion.py:183-188: every step
+    costs the same) on a BOUNDED sample of the workload: `batch` clip(s) of the largest
+    power-of-two length <= 2**18 for which warmup+steps units fit `budget_s` (probed at 2**14).
+    value = audio-seconds/sec of the full 50-step sampler extrapolated from that unit.  Shorter
+    clips are slightly CHEAPER per audio second (attention is quadratic in length), so a
+    bounded sample can only flatter the CPU arm."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reference_port as port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = port.DiffusionModelPort(**README)
-    x = torch.randn(batch, 2, LENGTH)
+
+    def one_step(length):
+        x = torch.randn(batch, 2, length)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            model.sample(x, num_steps=1)
+        return time.perf_counter() - t0
+
+    probe_len = 2 ** 14
+    one_step(probe_len)                       # thread pools / allocator warm
+    t_probe = one_step(probe_len)
+    length = probe_len
+    units = max(steps + warmup, 1)
+    while length < LENGTH and units * t_probe * (2 * length / probe_len) <= budget_s:
+        length *= 2
     times = []
     for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        x = model.sample(x, num_steps=1)
-        dt = time.perf_counter() - t0
+        dt = one_step(length)
         if i >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
-    value = batch * CLIP_SECONDS / (NUM_STEPS * per_step)
-    return value, per_step, cores, (f"{len(times)} x one VSampler step at batch {batch} "
-                                    f"([{batch},2,2**18], fp32, {cores} threads), x{NUM_STEPS} "
+    value = batch * CLIP_SECONDS * (length / LENGTH) / (NUM_STEPS * per_step)
+    return value, per_step, cores, (f"{len(times)} x one VSampler step on [{batch},2,{length}] fp32 "
+                                    f"({cores} threads; full clip is 2**18 = {LENGTH}), x{NUM_STEPS} "
                                     f"extrapolated to the 50-step sample")
 
 
@@ -131,9 +147,10 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     value, per_step, cores, sample = cpu_reference_run(args.steps, args.warmup)
+    # ms_per_step: one 50-step sample of the bench batch (8 clips) at the measured rate
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per_step * 1e3 * NUM_STEPS, "higher_is_better": True,
+            "ms_per_step": BATCH * CLIP_SECONDS / value * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": CONFIG,
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
@@ -320,7 +337,7 @@ def main():
         torch.cuda.empty_cache()
         line["train_step"] = train_step_bench(adp, dev, world, dist, steps=5, warmup=3)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        v, per_step, cores, sample = cpu_reference_run(steps=1, warmup=1)
+        v, per_step, cores, sample = cpu_reference_run(steps=1, warmup=1, budget_s=25.0)
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     if rank == 0:
