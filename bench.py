@@ -127,6 +127,12 @@ def cpu_reference_run(steps: int, warmup: int, budget_s: float = 150.0, batch: i
     # time-slice and every OpenMP barrier stalls (measured: 47 s per unit at 128 threads), so
     # the thread count is probed upwards from 8 on a short clip and the best one kept.
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                      # cgroup v2 CPU quota ("max 100000" = unlimited)
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            avail = max(1, min(avail, int(int(quota) / int(period))))
+    except Exception:
+        pass
     probe_len = 2 ** 14
     cores, t_probe = None, None
     for n in [c for c in (8, 16, 32, 64, 128, 256) if c < avail] + [avail]:
