@@ -175,7 +175,7 @@ def run_reference(args, rank: int):
                              "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 UPSAMPLER = dict(upsample_factor=16, in_channels=2,
@@ -231,6 +231,23 @@ NCU_DRAM_BYTES = {"conv_gemm[k3 M=2048 K=1024 N=1024x1]": 14776064.0,
 NCU_DRAM_SOURCE = "profiles/r1_ncu_conv_L7_v4.txt, profiles/r1_ncu_conv_L3_v4.txt"
 
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 from C (NCCL's version
+# banner) are sent to stderr for the duration of the run
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(text: str):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (text + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -244,6 +261,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -253,7 +271,6 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout (one JSON line)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -359,7 +376,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                 "sample": sample}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
