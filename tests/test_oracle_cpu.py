@@ -1,0 +1,120 @@
+"""The CPU oracle (oracle/reference_port.py over the oracle/a_unet shim) against the committed
+golden vectors.  The vectors were produced by oracle/make_golden.py in the build container, where
+the same script also proved the port bit-identical to the UNMODIFIED reference package; here
+(and on the GPU box, where /root/reference does not exist) the oracle is re-checked against them
+before any CUDA result is compared with it.  Same seeds as make_golden.py; tolerances are a few
+fp32 ulps of accumulated reordering noise (thread count / BLAS blocking may differ between
+machines), not bit-exactness."""
+import numpy as np
+import pytest
+import torch
+
+TINY = dict(in_channels=2, channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2],
+            attentions=[0, 0, 1], attention_heads=2, attention_features=64)
+TINY_TEXT = dict(TINY, cross_attentions=[0, 1, 1], use_embedding_cfg=True,
+                 embedding_max_length=8, embedding_features=32)
+TINY_NOATT = dict(channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+RTOL = 2e-5        # relative L2
+
+
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def fingerprint(module):
+    ps = [p.detach().double() for p in module.parameters()]
+    return np.array([sum(float(p.sum()) for p in ps), sum(float(p.abs().sum()) for p in ps),
+                     float(sum(p.numel() for p in ps))])
+
+
+def load(golden_dir, name):
+    return {k: v for k, v in np.load(f"{golden_dir}/{name}").items()}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(autouse=True)
+def _threads():
+    n = torch.get_num_threads()
+    torch.set_num_threads(min(n, 8))
+    yield
+    torch.set_num_threads(n)
+
+
+def test_sampler_algebra_toy_net(oracle_port, golden_dir):
+    """VSampler update algebra (reference diffusion.py:183-188) with a closed-form net."""
+    g = load(golden_dir, "sampler_toy.npz")
+
+    class Toy(torch.nn.Module):
+        def forward(self, x, t, **kw):
+            return 0.5 * x * t.view(-1, 1, 1) + torch.sin(x)
+
+    out = oracle_port.VSamplerPort(net=Toy())(t(g["x"]), num_steps=7)
+    assert rel_l2(out, t(g["out7"])) <= 1e-6
+
+
+def test_unconditional_forward_loss_grads_sampler(oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_unconditional.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(**TINY)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    x, sig = t(g["x"]), t(g["sigma"])
+    with torch.no_grad():
+        v = m.net(x, sig)
+    assert rel_l2(v, t(g["v"])) <= RTOL
+    torch.manual_seed(2)
+    loss = m(x)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    gnorm = torch.stack([p.grad.norm() for p in m.parameters()])
+    assert rel_l2(gnorm, t(g["grad_norms"])) <= 1e-4
+    grads = dict(m.named_parameters())
+    for key in [k for k in g if k.startswith("grad:")]:
+        got = grads[key[5:]].grad
+        assert rel_l2(got, t(g[key])) <= 1e-3, key
+    s = m.sample(t(g["noise"]), num_steps=5)
+    assert rel_l2(s, t(g["sample5"])) <= 1e-4
+
+
+def test_text_conditioning_and_cfg(oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_text_cfg.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(**TINY_TEXT)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    x, sig, emb = t(g["x"]), t(g["sigma"]), t(g["embedding"])
+    with torch.no_grad():
+        v1 = m.net(x, sig, embedding=emb)
+        v5 = m.net(x, sig, embedding=emb, embedding_scale=5.0)
+    assert rel_l2(v1, t(g["v_scale1"])) <= RTOL
+    assert rel_l2(v5, t(g["v_scale5"])) <= RTOL
+    s = m.sample(t(g["noise"]), num_steps=3, embedding=emb, embedding_scale=5.0)
+    assert rel_l2(s, t(g["sample3"])) <= 1e-4
+
+
+def test_upsampler_sample_loss_reupsample(oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_upsampler.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **TINY_NOATT)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    s = m.sample(t(g["low"]), num_steps=3, generator=torch.Generator().manual_seed(5))
+    assert rel_l2(s, t(g["sample3"])) <= 1e-4
+    audio = t(g["audio"])
+    torch.manual_seed(6)
+    loss = m(audio)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(m.reupsample(audio), t(g["reupsampled"])) <= 1e-6
+
+
+def test_vocoder_sample_and_loss(oracle_port, golden_dir):
+    g = load(golden_dir, "tiny_vocoder.npz")
+    kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True, **TINY_NOATT)
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionVocoderPort(**kw)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    s = m.sample(t(g["mel"]), num_steps=3, generator=torch.Generator().manual_seed(8))
+    assert rel_l2(s, t(g["sample3"])) <= 1e-4
+    torch.manual_seed(9)
+    loss = m(t(g["audio"]))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
