@@ -1,8 +1,13 @@
-"""User-facing model classes with the reference API (reference models.py:22-45, :134-224)."""
-from math import floor
-from typing import Callable, Optional
+"""The model classes users instantiate.  Same names, constructor keywords, attribute names
+(`net`, `diffusion`, `sampler`, `to_spectrogram`, `to_flat`) and call signatures as reference
+models.py:22-45 (DiffusionModel), :134-165 (DiffusionUpsampler), :168-224 (DiffusionVocoder);
+the arithmetic behind `net`, `diffusion` and `sampler` is the B200 path.  U-Net weights of a
+reference model are taken over with `model.net.load_reference_parameters(ref_model.net)`
+(same parameter order and shapes as a_unet's module tree)."""
+from typing import Callable, Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 from torch import Generator, Tensor, nn
 
 from .components import AppendChannelsPlugin, MelSpectrogram
@@ -12,19 +17,19 @@ from .utils import default, downsample, groupby, randn_like, upsample
 
 
 class DiffusionModel(nn.Module):
-    """reference models.py:22-45: `net_t`, `diffusion_t`, `sampler_t` plugin slots; kwargs with
-    the `diffusion_` / `sampler_` prefixes are routed to those, the rest builds the net, and
-    the same net object is shared by all three."""
+    """Three plugin slots around ONE shared net: `net_t(dim=..., **net kwargs)` builds it,
+    `diffusion_t(net=, loss_fn=, **diffusion_* kwargs)` is the training objective (`forward`),
+    `sampler_t(net=, **sampler_* kwargs)` the generation loop (`sample`, under no_grad)."""
 
     def __init__(self, net_t: Callable = UNetV0, diffusion_t: Callable = VDiffusion,
-                 sampler_t: Callable = VSampler, loss_fn: Callable = torch.nn.functional.mse_loss,
-                 dim: int = 1, **kwargs):
+                 sampler_t: Callable = VSampler, loss_fn: Callable = F.mse_loss, dim: int = 1,
+                 **kwargs):
         super().__init__()
-        diffusion_kwargs, kwargs = groupby("diffusion_", kwargs)
-        sampler_kwargs, kwargs = groupby("sampler_", kwargs)
-        self.net = net_t(dim=dim, **kwargs)
-        self.diffusion = diffusion_t(net=self.net, loss_fn=loss_fn, **diffusion_kwargs)
-        self.sampler = sampler_t(net=self.net, **sampler_kwargs)
+        for_diffusion, kwargs = groupby("diffusion_", kwargs)
+        for_sampler, net_kwargs = groupby("sampler_", kwargs)
+        self.net = net_t(dim=dim, **net_kwargs)
+        self.diffusion = diffusion_t(net=self.net, loss_fn=loss_fn, **for_diffusion)
+        self.sampler = sampler_t(net=self.net, **for_sampler)
 
     def forward(self, *args, **kwargs) -> Tensor:
         return self.diffusion(*args, **kwargs)
@@ -35,56 +40,59 @@ class DiffusionModel(nn.Module):
 
 
 class DiffusionUpsampler(DiffusionModel):
-    """reference models.py:134-165"""
+    """Band-limited copy of the target (down- then up-sampled by `upsample_factor`) as extra
+    input channels of the net; sampling starts from a low-rate waveform."""
 
     def __init__(self, in_channels: int, upsample_factor: int, net_t: Callable = UNetV0, **kwargs):
         self.upsample_factor = upsample_factor
-        super().__init__(net_t=AppendChannelsPlugin(net_t, channels=in_channels),
-                         in_channels=in_channels, **kwargs)
+        conditioned_net_t = AppendChannelsPlugin(net_t, channels=in_channels)
+        super().__init__(net_t=conditioned_net_t, in_channels=in_channels, **kwargs)
 
     def reupsample(self, x: Tensor) -> Tensor:
-        return upsample(downsample(x.clone(), factor=self.upsample_factor),
-                        factor=self.upsample_factor)
+        low = downsample(x.clone(), factor=self.upsample_factor)
+        return upsample(low, factor=self.upsample_factor)
 
     def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
-        return super().forward(x, *args, append_channels=self.reupsample(x), **kwargs)
+        kwargs["append_channels"] = self.reupsample(x)
+        return super().forward(x, *args, **kwargs)
 
     @torch.no_grad()
     def sample(self, downsampled: Tensor, generator: Optional[Generator] = None, **kwargs) -> Tensor:
-        reupsampled = upsample(downsampled, factor=self.upsample_factor)
-        noise = randn_like(reupsampled, generator=generator)
-        return super().sample(noise, append_channels=reupsampled, **kwargs)
+        guide = upsample(downsampled, factor=self.upsample_factor)
+        start = randn_like(guide, generator=generator)
+        return super().sample(start, append_channels=guide, **kwargs)
 
 
 class DiffusionVocoder(DiffusionModel):
-    """reference models.py:168-224: audio channels are folded into the batch; the mel
-    spectrogram is unrolled to a waveform-rate conditioning channel by a transposed conv."""
+    """Mel spectrogram -> waveform.  Every audio channel becomes its own batch row; a bias-free
+    transposed convolution (`to_flat`) stretches the spectrogram to one waveform-rate channel
+    that is appended to the net input."""
 
     def __init__(self, net_t: Callable = UNetV0, mel_channels: int = 80, mel_n_fft: int = 1024,
                  mel_hop_length: Optional[int] = None, mel_win_length: Optional[int] = None,
                  in_channels: int = 1, **kwargs):
-        mel_hop_length = default(mel_hop_length, floor(mel_n_fft) // 4)
-        mel_win_length = default(mel_win_length, mel_n_fft)
-        mel_kwargs, kwargs = groupby("mel_", kwargs)
+        hop = default(mel_hop_length, int(mel_n_fft) // 4)
+        win = default(mel_win_length, mel_n_fft)
+        front_end_kwargs, kwargs = groupby("mel_", kwargs)
         super().__init__(net_t=AppendChannelsPlugin(net_t, channels=1), in_channels=1, **kwargs)
-        self.to_spectrogram = MelSpectrogram(n_fft=mel_n_fft, hop_length=mel_hop_length,
-                                             win_length=mel_win_length,
-                                             n_mel_channels=mel_channels, **mel_kwargs)
-        self.to_flat = nn.ConvTranspose1d(in_channels=mel_channels, out_channels=1,
-                                          kernel_size=mel_win_length, stride=mel_hop_length,
-                                          padding=(mel_win_length - mel_hop_length) // 2,
-                                          bias=False)
+        self.to_spectrogram = MelSpectrogram(n_fft=mel_n_fft, hop_length=hop, win_length=win,
+                                             n_mel_channels=mel_channels, **front_end_kwargs)
+        self.to_flat = nn.ConvTranspose1d(mel_channels, 1, kernel_size=win, stride=hop,
+                                          padding=(win - hop) // 2, bias=False)
+
+    def _unroll(self, spectrogram: Tensor) -> Tuple[Tensor, torch.Size]:
+        """[..., mel, frames] -> ([rows, 1, samples], leading shape)."""
+        lead = spectrogram.shape[:-2]
+        return self.to_flat(spectrogram.reshape(-1, *spectrogram.shape[-2:])), lead
 
     def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
-        spec = self.to_spectrogram(x)                                   # [b, c, f, l]
-        flat = self.to_flat(spec.reshape(-1, *spec.shape[-2:]))         # [(b c), 1, t]
-        x = x.reshape(-1, 1, x.shape[-1])
-        return super().forward(x, *args, append_channels=flat, **kwargs)
+        guide, _ = self._unroll(self.to_spectrogram(x))
+        rows = x.reshape(-1, 1, x.shape[-1])
+        return super().forward(rows, *args, append_channels=guide, **kwargs)
 
     @torch.no_grad()
     def sample(self, spectrogram: Tensor, generator: Optional[Generator] = None, **kwargs) -> Tensor:
-        lead = spectrogram.shape[:-2]
-        flat = self.to_flat(spectrogram.reshape(-1, *spectrogram.shape[-2:]))
-        noise = randn_like(flat, generator=generator)
-        wave = super().sample(noise, append_channels=flat, **kwargs)
-        return wave.reshape(*lead, wave.shape[-1])
+        guide, lead = self._unroll(spectrogram)
+        start = randn_like(guide, generator=generator)
+        rows = super().sample(start, append_channels=guide, **kwargs)
+        return rows.reshape(*lead, rows.shape[-1])

@@ -1,50 +1,71 @@
-"""Host-side helpers of the hot path (reference utils.py): kwarg routing, the windowed-sinc
-resampler used once per DiffusionUpsampler call, CPU-generator randn."""
-from math import ceil, pi
-from typing import Dict, Optional, Tuple
+"""Host-side helpers around the hot path: keyword routing for the plugin slots, the polyphase
+windowed-sinc resampler behind DiffusionUpsampler (one strided convolution per call, outside
+the step loop; its filter bank is built once per (factors, dtype, device) and cached), and the
+CPU-generator noise draw.  Behavioural spec: reference utils.py:17-125."""
+import functools
+import math
+from typing import Any, Callable, Dict, Optional, Tuple, Union
 
 import torch
 import torch.nn.functional as F
 from torch import Generator, Tensor
 
 
-def exists(val) -> bool:
+def exists(val: Any) -> bool:
     return val is not None
 
 
-def default(val, d):
-    if exists(val):
+def default(val: Any, fallback: Union[Any, Callable[[], Any]]) -> Any:
+    """`val` unless it is None; a callable fallback (not a class) is evaluated lazily."""
+    if val is not None:
         return val
-    return d() if callable(d) and not isinstance(d, type) else d
+    lazy = callable(fallback) and not isinstance(fallback, type)
+    return fallback() if lazy else fallback
 
 
-def groupby(prefix: str, d: Dict, keep_prefix: bool = False) -> Tuple[Dict, Dict]:
-    """Splits kwargs on a prefix (reference utils.py:48-70): (`prefix*` stripped, the rest)."""
-    with_prefix = {k: v for k, v in d.items() if k.startswith(prefix)}
-    rest = {k: v for k, v in d.items() if not k.startswith(prefix)}
-    if not keep_prefix:
-        with_prefix = {k[len(prefix):]: v for k, v in with_prefix.items()}
-    return with_prefix, rest
+def groupby(prefix: str, d: Dict[str, Any], keep_prefix: bool = False) -> Tuple[Dict, Dict]:
+    """Partition keyword arguments: ({keys that start with `prefix`, prefix removed unless
+    keep_prefix}, {all others}) — how `diffusion_*`, `sampler_*` and `mel_*` options reach their
+    plugin (reference utils.py:48-70)."""
+    taken: Dict[str, Any] = {}
+    others: Dict[str, Any] = {}
+    cut = 0 if keep_prefix else len(prefix)
+    for key, value in d.items():
+        if key.startswith(prefix):
+            taken[key[cut:]] = value
+        else:
+            others[key] = value
+    return taken, others
+
+
+@functools.lru_cache(maxsize=32)
+def _polyphase_bank(factor_in: int, factor_out: int, rolloff: float, zeros: int, dtype: torch.dtype,
+                    device: str) -> Tuple[Tensor, int]:
+    """FIR bank [factor_out, 1, taps] of the Hann-windowed sinc low-pass at `rolloff` x Nyquist
+    of the slower rate, one phase per output sample inside an input period, and the half width
+    (in input samples) the signal has to be padded by.  The expression order follows the
+    oracle's (bit-identical filters)."""
+    opts = dict(device=torch.device(device), dtype=dtype)
+    cutoff = min(factor_in, factor_out) * rolloff
+    half = math.ceil(zeros * factor_in / cutoff)
+    grid = torch.arange(-half, half + factor_in, **opts)[None, None] / factor_in
+    theta = torch.arange(0, -factor_out, step=-1, **opts)[:, None, None] / factor_out + grid
+    theta = (theta * cutoff).clamp(-zeros, zeros) * math.pi
+    hann = torch.cos(theta / zeros / 2) ** 2
+    sinc = torch.where(theta == 0, torch.tensor(1.0).to(theta), theta.sin() / theta)
+    return sinc * (hann * (cutoff / factor_in)), half
 
 
 def resample(waveforms: Tensor, factor_in: int, factor_out: int, rolloff: float = 0.99,
              lowpass_filter_width: int = 6) -> Tensor:
-    """Windowed-sinc polyphase resampling (reference utils.py:82-109): one strided conv with
-    `factor_out` FIR phases, interleaved.  Runs once per call, outside the step loop."""
-    b, c, length = waveforms.shape
-    n_out = int(factor_out * length / factor_in)
-    kw = dict(device=waveforms.device, dtype=waveforms.dtype)
-    base = min(factor_in, factor_out) * rolloff
-    width = ceil(lowpass_filter_width * factor_in / base)
-    taps = torch.arange(-width, width + factor_in, **kw)[None, None] / factor_in
-    phase = torch.arange(0, -factor_out, step=-1, **kw)[:, None, None] / factor_out
-    t = ((phase + taps) * base).clamp(-lowpass_filter_width, lowpass_filter_width) * pi
-    window = torch.cos(t / lowpass_filter_width / 2) ** 2
-    fir = torch.where(t == 0, torch.ones_like(t), t.sin() / t) * (window * (base / factor_in))
-    x = F.pad(waveforms.reshape(b * c, 1, length), (width, width + factor_in))
-    y = F.conv1d(x, fir, stride=factor_in)                      # [(b c), factor_out, frames]
-    y = y.transpose(1, 2).reshape(b, c, -1)                      # interleave the phases
-    return y[..., :n_out]
+    """[b, c, t] -> [b, c, t * factor_out / factor_in]."""
+    b, c, t = waveforms.shape
+    bank, half = _polyphase_bank(int(factor_in), int(factor_out), float(rolloff),
+                                 int(lowpass_filter_width), waveforms.dtype, str(waveforms.device))
+    rows = F.pad(waveforms.reshape(b * c, t), (half, half + factor_in))
+    phases = F.conv1d(rows[:, None], bank, stride=factor_in)             # [(b c), factor_out, frames]
+    woven = phases.reshape(b, c, factor_out, -1).permute(0, 1, 3, 2).reshape(b, c, -1)
+    return woven[..., : int(factor_out * t / factor_in)]
 
 
 def downsample(waveforms: Tensor, factor: int, **kwargs) -> Tensor:
@@ -56,5 +77,6 @@ def upsample(waveforms: Tensor, factor: int, **kwargs) -> Tensor:
 
 
 def randn_like(tensor: Tensor, *args, generator: Optional[Generator] = None, **kwargs) -> Tensor:
-    """reference utils.py:123-125: drawn on the CPU generator, then moved to `tensor`."""
+    """Gaussian noise shaped like `tensor`, drawn on the CPU generator (so a seed reproduces
+    the reference's samples on any device) and then moved to `tensor`'s device and dtype."""
     return torch.randn(tensor.shape, *args, generator=generator, **kwargs).to(tensor)

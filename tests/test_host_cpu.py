@@ -79,3 +79,77 @@ def test_product_path_refuses_to_run_on_cpu():
                                items=[1, 1], attentions=[0, 0])
     with pytest.raises((AssertionError, RuntimeError)):
         model.sample(torch.randn(1, 2, 64), num_steps=2)
+
+
+def test_resampler_matches_the_oracle(oracle_port):
+    """utils.resample (cached polyphase bank) == the oracle's windowed-sinc resampler, which
+    make_golden.py proved bit-identical to the reference's."""
+    from audio_diffusion_pytorch_b200 import utils
+    torch.manual_seed(3)
+    x = torch.randn(2, 2, 512)
+    for f in (2, 4, 16):
+        assert torch.equal(utils.upsample(x, f), oracle_port.sinc_upsample(x, f))
+        assert torch.equal(utils.downsample(x, f), oracle_port.sinc_downsample(x, f))
+    assert torch.equal(utils.upsample(x, 4), utils.upsample(x, 4))       # cached bank, same result
+    y = utils.resample(x, 3, 2)
+    assert torch.equal(y, oracle_port.sinc_resample(x, 3, 2))
+
+
+def test_kwarg_routing_helpers():
+    from audio_diffusion_pytorch_b200.utils import default, groupby
+    taken, rest = groupby("mel_", {"mel_n_fft": 64, "channels": [8], "mel_sample_rate": 48000})
+    assert taken == {"n_fft": 64, "sample_rate": 48000} and rest == {"channels": [8]}
+    kept, _ = groupby("mel_", {"mel_n_fft": 64}, keep_prefix=True)
+    assert kept == {"mel_n_fft": 64}
+    assert default(None, 3) == 3 and default(0, 3) == 0 and default(None, lambda: 7) == 7
+    assert default(None, int) is int          # classes are values, not factories
+
+
+def test_model_classes_take_over_reference_parameters(oracle_port):
+    """The U-Net registers its parameters in a_unet's order with a_unet's shapes, so
+    `load_reference_parameters` can adopt the weights of a reference model; the vocoder's own
+    layers keep the reference's names."""
+    import audio_diffusion_pytorch_b200 as adp
+    tiny = dict(channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+    voc_kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True, **tiny)
+    pairs = [
+        (adp.DiffusionModel(net_t=adp.UNetV0, in_channels=2, attentions=[0, 0, 1], attention_heads=2,
+                            attention_features=64, **tiny),
+         oracle_port.DiffusionModelPort(in_channels=2, attentions=[0, 0, 1], attention_heads=2,
+                                        attention_features=64, **tiny)),
+        (adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2, **tiny),
+         oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **tiny)),
+        (adp.DiffusionVocoder(net_t=adp.UNetV0, **voc_kw), oracle_port.DiffusionVocoderPort(**voc_kw)),
+    ]
+    for ours, ref in pairs:
+        want = [tuple(p.shape) for p in ref.net.parameters()]
+        got = [tuple(p.shape) for p in ours.net.parameters()]
+        assert got == want
+        ours.net.load_reference_parameters(ref.net)
+        for a, b in zip(ours.net.parameters(), ref.net.parameters()):
+            assert torch.equal(a, b)
+        assert ours.diffusion.net is ours.net and ours.sampler.net is ours.net
+    voc, vref = pairs[2]
+    for key in ("to_flat.weight",):
+        assert voc.state_dict()[key].shape == vref.state_dict()[key].shape
+
+
+def test_upsampler_and_vocoder_conditioning_paths(oracle_port):
+    """Host-side halves of DiffusionUpsampler / DiffusionVocoder (everything before the net)."""
+    import audio_diffusion_pytorch_b200 as adp
+    tiny = dict(channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+    up = adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2, **tiny)
+    ref = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **tiny)
+    x = torch.randn(2, 2, 4096)
+    assert torch.equal(up.reupsample(x), ref.reupsample(x))
+    kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True, **tiny)
+    torch.manual_seed(0)
+    voc = adp.DiffusionVocoder(net_t=adp.UNetV0, **kw)
+    vref = oracle_port.DiffusionVocoderPort(**kw)
+    voc.to_flat.load_state_dict(vref.to_flat.state_dict())
+    mel = torch.randn(2, 2, 8, 256)
+    guide, lead = voc._unroll(mel)
+    assert lead == (2, 2) and guide.shape == (4, 1, 4096)
+    assert torch.equal(guide, vref.to_flat(mel.reshape(-1, 8, 256)))
+    audio = torch.randn(2, 2, 4096)
+    assert torch.allclose(voc.to_spectrogram(audio), vref.to_spectrogram(audio), atol=1e-6)
