@@ -237,6 +237,7 @@ class B200UNet(nn.Module):
         # C = 32 / 64 ConvBlocks as ONE fused kernel (GroupNorm+SiLU -> conv3 -> +res -> LN/FiLM ->
         # statistics, csrc/mid_conv.cu) instead of three: those levels are HBM-bound
         self.fuse_thin_levels = True
+        self.cond_table_rows = 4096    # sampler: rows (steps x batch) of conditioning per pass
 
     # ------------------------------------------------------------------ weights
     def levels(self) -> List[LevelParams]:
@@ -762,12 +763,18 @@ class B200UNet(nn.Module):
         num_steps = sigmas.shape[0] - 1
         ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], dim=1).float().contiguous()
         sig = sigmas.float().repeat(1, Bh // B).contiguous()      # [N+1, Bh]
-        feats = plan.features_in.repeat(num_steps, 1) if plan.use_features_in else None
-        table = self._cond_table(sig[:num_steps].reshape(-1), feats).view(num_steps, Bh, -1)
+        # conditioning table in blocks of <= ~4096 rows (190 KB of fp32 per row for the README net)
+        block = max(1, self.cond_table_rows // Bh)
+        table, first = None, 0
         steps = range(num_steps) if progress is None else progress
         for i in steps:   # two small device copies + one graph launch per step, no host sync
+            if table is None or not (first <= i < first + table.shape[0]):
+                first = (i // block) * block
+                n = min(block, num_steps - first)
+                feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
+                table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
             plan.ab.copy_(ab[i], non_blocking=True)
-            plan.ss_all.copy_(table[i], non_blocking=True)
+            plan.ss_all.copy_(table[i - first], non_blocking=True)
             self._execute(plan)
         return plan.x.clone().to(x_noisy.dtype)
 
