@@ -58,14 +58,21 @@ class StemOutBwdArgs(C.Structure):
     _fields_ = [("dv", vp), ("gscale", vp), ("h", vp), ("x", vp), ("append", vp), ("noise", vp),
                 ("alpha", vp), ("beta", vp), ("w", vp), ("bias", vp), ("w_adapt", vp), ("gate", vp),
                 ("dh", vp), ("dw", vp), ("dbias", vp), ("dgate", vp), ("dw_adapt", vp),
-                ("db_adapt", vp), ("B", i32), ("T", i32), ("cx", i32), ("ca", i32), ("c0", i32),
+                ("db_adapt", vp), ("dxin", vp), ("B", i32), ("T", i32), ("cx", i32), ("ca", i32), ("c0", i32),
                 ("co", i32), ("f", i32), ("ld_gate", i32), ("ld_dgate", i32)]
 
 
 class StemInBwdArgs(C.Structure):
     _fields_ = [("dout", vp), ("x", vp), ("append", vp), ("noise", vp), ("alpha", vp), ("beta", vp),
-                ("dw", vp), ("dbias", vp), ("B", i32), ("T", i32), ("cx", i32), ("ca", i32),
-                ("c0", i32), ("f", i32)]
+                ("dw", vp), ("dbias", vp), ("w", vp), ("dxin", vp), ("B", i32), ("T", i32),
+                ("cx", i32), ("ca", i32), ("c0", i32), ("f", i32)]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [("q", vp), ("k", vp), ("v", vp), ("o", vp), ("d_o", vp), ("lse", vp), ("delta", vp),
+                ("dq", vp), ("dk", vp), ("dv", vp), ("B", i32), ("H", i32), ("Tq", i32), ("Tk", i32),
+                ("ldq", i32), ("ldk", i32), ("ldv", i32), ("ldo", i32), ("lddo", i32), ("lddq", i32),
+                ("lddk", i32), ("lddv", i32), ("scale", f32)]
 
 
 _lib = None
@@ -91,7 +98,9 @@ def lib() -> C.CDLL:
         "adp_gn_stats": [vp, vp, i32, i32, i32, i32, vp],
         "adp_ln_film": [vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, vp],
         "adp_ln_film_dual": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, f32, f32, vp],
-        "adp_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+        "adp_attention": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp],
+        "adp_attention_bwd": [C.POINTER(AttentionBwdArgs), vp],
+        "adp_ln_fold_bwd": [vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp],
         "adp_skinny_linear": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
         "adp_time_features": [vp, vp, vp, i32, i32, i32, vp],
         "adp_stem_in": [C.POINTER(StemInArgs), vp],
@@ -102,7 +111,7 @@ def lib() -> C.CDLL:
         "adp_wgrad": [C.POINTER(WgradArgs), vp],
         "adp_gn_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "adp_gn_bwd_apply": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
-        "adp_ln_film_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, f32, vp],
+        "adp_ln_film_bwd": [vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, f32, vp],
         "adp_colsum": [vp, vp, i32, vp, i32, i32, i32, vp],
         "adp_skip_gate": [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
         "adp_skip_gate_bwd": [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, vp],
@@ -131,4 +140,4 @@ EXPORTS = ["adp_version", "adp_last_error", "adp_device_check", "adp_conv_gemm",
            "adp_sampler_step", "adp_silu_bf16", "adp_debug_set", "adp_wgrad", "adp_gn_silu_bwd",
            "adp_gn_bwd_apply", "adp_ln_film_bwd", "adp_colsum", "adp_skip_gate",
            "adp_skip_gate_bwd", "adp_cond_bwd", "adp_narrow_conv_bwd", "adp_stem_out_bwd",
-           "adp_stem_in_bwd"]
+           "adp_stem_in_bwd", "adp_attention_bwd", "adp_ln_fold_bwd"]

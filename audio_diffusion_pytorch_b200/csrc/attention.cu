@@ -28,6 +28,7 @@ constexpr int kSoftmaxThreads = 256;
 
 struct AttnParams {
   __nv_bfloat16* o;
+  float* lse;         // optional [B][H][Tq]: log-sum-exp of the scaled scores (training forward)
   int Tq, Tk, ldo;
   float scale_log2;   // scale * log2(e)
 };
@@ -217,8 +218,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_after();
     s_xch[half][row] = l_run;
     named_bar_sync(2, kSoftmaxThreads);
-    const float inv_l = 1.f / (l_run + s_xch[half ^ 1][row]);
+    const float l_tot = l_run + s_xch[half ^ 1][row];
+    const float inv_l = 1.f / l_tot;
     const int t = t0 + row;
+    if (p.lse != nullptr && half == 0 && t < p.Tq)    // natural-log units (adp_attention_bwd)
+      p.lse[(static_cast<size_t>(b) * gridDim.y + h) * p.Tq + t] =
+          (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f;
     uint32_t o[32];
     tmem_ld32(tmem_o + lane_off + half * 32, o);
     tmem_ld_wait();
@@ -250,7 +255,8 @@ using namespace adp;
 
 extern "C" int adp_attention(const void* q, const void* k, const void* v, void* o, int32_t B,
                              int32_t H, int32_t Tq, int32_t Tk, int32_t ldq, int32_t ldk,
-                             int32_t ldv, int32_t ldo, float scale, adp_stream_t stream) {
+                             int32_t ldv, int32_t ldo, float scale, float* lse,
+                             adp_stream_t stream) {
   ADP_CHECK(q && k && v && o, "adp_attention: null pointer");
   ADP_CHECK(B > 0 && H > 0 && Tq > 0 && Tk > 0, "adp_attention: bad sizes");
   ADP_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && ldq >= H * kD &&
@@ -274,14 +280,11 @@ extern "C" int adp_attention(const void* q, const void* k, const void* v, void* 
     const uint64_t str[2] = {(uint64_t)ldv * 2, (uint64_t)Tk * ldv * 2};
     if (int e = make_tmap_bf16(&tmV, v, 3, dims, str, box, 128)) return e;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kAttnSmem));
-    attr_set = true;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(attention_kernel, (size_t)kAttnSmem, smem_cache));
   AttnParams p;
   p.o = static_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
   p.Tq = Tq;
   p.Tk = Tk;
   p.ldo = ldo;

@@ -189,8 +189,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 ln_film_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                    const float* __restrict__ ss, int ss_stride, uint4* __restrict__ dx,
-                   float* __restrict__ dss, int dss_stride, float* __restrict__ colsum, int T,
-                   int C, int lpr, float eps) {
+                   float* __restrict__ dss, int dss_stride, float* __restrict__ colsum,
+                   const uint4* __restrict__ dres, int T, int C, int lpr, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ __align__(16) float s_fs[kBwMaxC];
@@ -262,6 +262,12 @@ ln_film_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rstd * (vg[it][j] - m1 - vx[it][j] * m2);
+      if (dres != nullptr && ok) {        // gradient arriving on a parallel (residual) path
+        float fr[8];
+        unpack8(__ldg(dres + boff + static_cast<size_t>(row) * vpr + it * lpr + l), fr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += fr[j];
+      }
       const uint4 ov = pack8(o);
       if (ok) {
         dx[boff + static_cast<size_t>(row) * vpr + it * lpr + l] = ov;
@@ -306,12 +312,13 @@ ln_film_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------- colsum
+constexpr int kColsumMaxC = 2048;     // fused q|k|v gradient rows are 3*512 wide
 __global__ void __launch_bounds__(256)
 colsum_kernel(const uint4* __restrict__ x, const float* __restrict__ gate, int ld_gate,
               float* __restrict__ out, int T, int C) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_cs[kBwMaxC];
+  __shared__ float s_cs[kColsumMaxC];
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) s_cs[c] = 0.f;
   __syncthreads();
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(256)
 cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restrict__ cond,
                 const __nv_bfloat16* __restrict__ w, float* __restrict__ dw,
                 float* __restrict__ dbias, float* __restrict__ dcond, int B, int N, int K,
-                int rows_per_block) {
+                int rows_per_block, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_buf[];     // cond [B][K], then dss slab [B][rows_per_block]
@@ -454,7 +461,7 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
   if (threadIdx.x < nr) {
     float t = 0.f;
     for (int bb = 0; bb < B; ++bb) t += s_d[bb * rows_per_block + threadIdx.x];
-    dbias[n0 + threadIdx.x] = t;
+    dbias[n0 + threadIdx.x] = accumulate ? dbias[n0 + threadIdx.x] + t : t;
   }
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float dc[kCondMaxB];
@@ -471,7 +478,8 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
           dc[bb] += d * wv;
         }
       }
-      dw[static_cast<size_t>(n0 + r) * K + k] = g;
+      float* dwp = dw + static_cast<size_t>(n0 + r) * K + k;
+      *dwp = accumulate ? *dwp + g : g;
     }
 #pragma unroll
     for (int bb = 0; bb < kCondMaxB; ++bb)
@@ -521,8 +529,8 @@ extern "C" int adp_gn_bwd_apply(const void* dxh, const void* x, const double* st
 
 extern "C" int adp_ln_film_bwd(const void* dy, const void* x, const float* scale_shift,
                                int32_t ss_stride, void* dx, float* dss, int32_t dss_stride,
-                               float* colsum, int32_t B, int32_t T, int32_t C, float eps,
-                               adp_stream_t stream) {
+                               float* colsum, const void* dres, int32_t B, int32_t T, int32_t C,
+                               float eps, adp_stream_t stream) {
   ADP_CHECK(dy && x && dx, "adp_ln_film_bwd: null");
   ADP_CHECK(C % 8 == 0 && C <= kBwMaxC, "adp_ln_film_bwd: C=%d", C);
   const int vpr = C / 8;
@@ -545,7 +553,8 @@ extern "C" int adp_ln_film_bwd(const void* dy, const void* x, const float* scale
   cudaStream_t s = as_stream(stream);
 #define ADP_LNB(VPL)                                                                              \
   ADP_CUDA(launch_k(ln_film_bwd_kernel<VPL>, grid, dim3(256), (size_t)0, s, pdy, px, scale_shift, \
-                    (int)ss_stride, pdx, dss, (int)dss_stride, colsum, (int)T, (int)C, (int)lpr, eps))
+                    (int)ss_stride, pdx, dss, (int)dss_stride, colsum,                            \
+                    static_cast<const uint4*>(dres), (int)T, (int)C, (int)lpr, eps))
   if (vpl == 1) ADP_LNB(1);
   else if (vpl == 2) ADP_LNB(2);
   else if (vpl == 3) ADP_LNB(3);
@@ -556,7 +565,7 @@ extern "C" int adp_ln_film_bwd(const void* dy, const void* x, const float* scale
 
 extern "C" int adp_colsum(const void* x, const float* gate, int32_t ld_gate, float* out, int32_t B,
                           int32_t T, int32_t C, adp_stream_t stream) {
-  ADP_CHECK(x && out && C % 8 == 0 && C <= kBwMaxC, "adp_colsum: bad args (C=%d)", C);
+  ADP_CHECK(x && out && C % 8 == 0 && C <= kColsumMaxC, "adp_colsum: bad args (C=%d)", C);
   dim3 grid(grid_for(static_cast<size_t>(T) * (C / 8), B), B);
   ADP_CUDA(launch_k(colsum_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
                     static_cast<const uint4*>(x), gate, (int)ld_gate, out, (int)T, (int)C));
@@ -590,17 +599,20 @@ extern "C" int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond,
                             float* dw, float* dbias, float* dcond, int32_t B, int32_t N, int32_t K,
                             adp_stream_t stream) {
   ADP_CHECK(dss && cond && w && dw && dbias && dcond, "adp_cond_bwd: null");
-  ADP_CHECK(B >= 1 && B <= kCondMaxB, "adp_cond_bwd: B=%d > %d", B, kCondMaxB);
+  ADP_CHECK(B >= 1, "adp_cond_bwd: B=%d", B);
   const int rows_per_block = 64;
-  const size_t smem = (static_cast<size_t>(B) * K + static_cast<size_t>(B) * rows_per_block) * sizeof(float);
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(cond_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
   dim3 grid((N + rows_per_block - 1) / rows_per_block);
-  ADP_CUDA(launch_k(cond_bwd_kernel, grid, dim3(256), smem, as_stream(stream), dss, (int)ld_dss, cond,
-                    static_cast<const __nv_bfloat16*>(w), dw, dbias, dcond, (int)B, (int)N, (int)K,
-                    (int)rows_per_block));
+  // batches beyond kCondMaxB rows run as further passes that accumulate into dw / dbias
+  for (int b0 = 0; b0 < B; b0 += kCondMaxB) {
+    const int bc = B - b0 < kCondMaxB ? B - b0 : kCondMaxB;
+    const size_t smem = (static_cast<size_t>(bc) * K + static_cast<size_t>(bc) * rows_per_block) * sizeof(float);
+    ADP_CUDA(ensure_dyn_smem(cond_bwd_kernel, smem, smem_cache));
+    ADP_CUDA(launch_k(cond_bwd_kernel, grid, dim3(256), smem, as_stream(stream),
+                      dss + static_cast<size_t>(b0) * ld_dss, (int)ld_dss,
+                      cond + static_cast<size_t>(b0) * K, static_cast<const __nv_bfloat16*>(w), dw,
+                      dbias, dcond + static_cast<size_t>(b0) * K, (int)bc, (int)N, (int)K,
+                      (int)rows_per_block, (int)(b0 > 0)));
+  }
   return 0;
 }

@@ -34,6 +34,22 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 inline cudaStream_t as_stream(adp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest
+// value set so far for each device (one static cache per kernel instantiation at the call site).
+struct SmemAttrCache { size_t set[64] = {}; };
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kernel, size_t bytes, SmemAttrCache& cache) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  size_t& cur = cache.set[dev & 63];
+  if (cur == 0) cur = 48 * 1024;               // the default limit needs no opt-in
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 // Every kernel is launched with the programmatic-dependent-launch attribute: kernel N+1 may
 // start (set up smem / mbarriers / TMEM, prefetch tensor maps) while kernel N drains; it calls
 // griddepcontrol.wait before its first global-memory access.  adp_debug_set(6, 0) disables.

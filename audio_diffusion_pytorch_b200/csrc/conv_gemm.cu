@@ -24,9 +24,7 @@
 
 namespace adp {
 
-int conv_gemm_v1(const adp_conv_gemm_args* args, adp_stream_t stream);
-
-// A/B + diagnostic switches (adp_debug_set): [0] impl 2=persistent 1=v1; [2] 1 = weights are not
+// diagnostic switches (adp_debug_set): [0] unused; [2] 1 = weights are not
 // written by the preceding kernels (fetch them before griddepcontrol.wait); [3] CTAs/SM override;
 // [4] bit0 skip MMAs, bit1 skip TMA loads, bit2 skip drain, bit3 exit at entry (timing
 // experiments only); [5] KC override; [6] PDL; [7] 1 = never use the 8-epilogue-warp variant
@@ -668,12 +666,8 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
     if (int e = make_tmap_bf16(&tmW, a.w, 2, dims, strides, box, SW)) return e;
   }
 
-  static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, SW, XF, EW>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(conv_gemm2_kernel<BN, SW, XF, EW>, smem, smem_cache));
 
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.residual = static_cast<const __nv_bfloat16*>(a.residual);
@@ -748,7 +742,6 @@ extern "C" int adp_debug_set(int key, int value) {
 
 extern "C" int adp_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream) {
   using namespace adp;
-  if (g_debug[0] == 1) return conv_gemm_v1(args, stream);
   ADP_CHECK(args != nullptr, "adp_conv_gemm: null args");
   const adp_conv_gemm_args& a = *args;
   ADP_CHECK(a.a && a.w && a.out, "adp_conv_gemm: null a/w/out");

@@ -303,12 +303,8 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
 template <int C>
 static int launch_mid(const adp_narrow_conv_args& a, cudaStream_t stream) {
   using Cfg = MidCfg<C>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ADP_CUDA(cudaFuncSetAttribute(mid_conv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  Cfg::SMEM));
-    attr_set = true;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(mid_conv_kernel<C>, (size_t)Cfg::SMEM, smem_cache));
   int dev = 0, sms = 148, occ = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

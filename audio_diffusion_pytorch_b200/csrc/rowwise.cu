@@ -567,12 +567,8 @@ extern "C" int adp_skinny_linear(const float* x, const void* w, const float* bia
   ADP_CHECK(K % 8 == 0 && ldw % 8 == 0 && K <= 3072 && K <= ldx && K <= ldw,
             "adp_skinny_linear: K=%d ldx=%d ldw=%d unsupported", K, ldx, ldw);
   const size_t smem = static_cast<size_t>(kSkinnyRows) * K * sizeof(float);
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(skinny_linear_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(skinny_linear_kernel, smem, smem_cache));
   dim3 grid(pick_grid(N, 8, 148 * 2), (B + kSkinnyRows - 1) / kSkinnyRows);
   ADP_CUDA(launch_k(skinny_linear_kernel, grid, dim3(256), smem, as_stream(stream), x,
                     static_cast<const __nv_bfloat16*>(w), bias, y, (int)B, (int)K, (int)N, (int)ldx,

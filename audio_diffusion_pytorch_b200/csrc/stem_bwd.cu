@@ -268,6 +268,22 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
       atomicAdd(a.db_adapt + o, acc);
     }
   }
+  // (3) gradient w.r.t. the net input through the skip path (v = skip(x_in) + gate*y):
+  // identity skip -> dv, SkipAdapter -> W_adapt^T dv.  Plain stores: adp_stem_in_bwd adds the
+  // DownsampleItem path afterwards.
+  if (a.dxin != nullptr) {
+    for (int i = threadIdx.x; i < kTB * cin; i += kTB) {
+      const int c = i / kTB, r = i - c * kTB;
+      if (r >= nvalid) continue;
+      float acc = 0.f;
+      if (a.w_adapt != nullptr) {
+        for (int o = 0; o < a.co; ++o) acc += s_dv[r * a.co + o] * a.w_adapt[o * cin + c];
+      } else if (c < a.co) {
+        acc = s_dv[r * a.co + c];
+      }
+      a.dxin[(static_cast<size_t>(b) * cin + c) * a.T + t0 + r] = acc;
+    }
+  }
 }
 
 // -------------------------------------------------------------------------- stem_in_bwd
@@ -317,6 +333,19 @@ __global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_
       atomicAdd(a.dbias + o, acc);
     }
   }
+  // gradient w.r.t. cat([x, append]) through the k = s = f DownsampleItem, ADDED to what
+  // adp_stem_out_bwd stored: dxin[b][c][to*f + j] += sum_o dout[b][to][o] * w[o][c][j]
+  if (a.dxin != nullptr) {
+    for (int i = threadIdx.x; i < kTB * ci_total; i += kTB) {
+      const int c = i / (kTB * a.f), rem = i - c * kTB * a.f, r = rem / a.f, j = rem - r * a.f;
+      const int to = to0 + r;
+      if (to >= To) continue;
+      float acc = 0.f;
+      const float* wp = a.w + c * a.f + j;
+      for (int o = 0; o < a.c0; ++o) acc += s_g[r * a.c0 + o] * __ldg(wp + o * ci_total);
+      a.dxin[(static_cast<size_t>(b) * cin + c) * a.T + static_cast<size_t>(to) * a.f + j] += acc;
+    }
+  }
 }
 
 }  // namespace adp
@@ -347,11 +376,8 @@ extern "C" int adp_stem_out_bwd(const adp_stem_out_bwd_args* args, adp_stream_t 
   const size_t smem = (static_cast<size_t>(a.co) * 3 * a.c0 + static_cast<size_t>(rows_h) * a.c0 +
                        static_cast<size_t>(kTB + 2) * a.co + static_cast<size_t>(kTB) * a.co +
                        static_cast<size_t>(kTB) * cin) * sizeof(float);
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(stem_out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(stem_out_bwd_kernel, smem, smem_cache));
   dim3 grid((a.T + kTB - 1) / kTB, a.B);
   ADP_CUDA(launch_k(stem_out_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
   return 0;
@@ -363,12 +389,10 @@ extern "C" int adp_stem_in_bwd(const adp_stem_in_bwd_args* args, adp_stream_t st
   ADP_CHECK((a.cx + a.ca) * a.f <= 32 && a.c0 % 8 == 0 && a.c0 <= 64 && a.T % a.f == 0,
             "adp_stem_in_bwd: unsupported sizes");
   ADP_CHECK((a.ca == 0) == (a.append == nullptr), "adp_stem_in_bwd: append / ca mismatch");
+  ADP_CHECK(!a.dxin || a.w, "adp_stem_in_bwd: dxin needs the conv weights");
   const size_t smem = (static_cast<size_t>(kTB) * (a.cx + a.ca) * a.f + static_cast<size_t>(kTB) * a.c0) * sizeof(float);
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(stem_in_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(stem_in_bwd_kernel, smem, smem_cache));
   dim3 grid((a.T / a.f + kTB - 1) / kTB, a.B);
   ADP_CUDA(launch_k(stem_in_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
   return 0;

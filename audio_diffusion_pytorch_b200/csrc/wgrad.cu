@@ -194,12 +194,8 @@ static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
   splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   const size_t smem = static_cast<size_t>(n_stages) * STAGE_BYTES + 1024;
-  static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    ADP_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    smem_attr = smem;
-  }
+  static SmemAttrCache smem_cache;
+  ADP_CUDA(ensure_dyn_smem(wgrad_kernel<BN>, smem, smem_cache));
   dim3 grid(n_tiles, k_tiles, splits);
   ADP_CUDA(launch_k(wgrad_kernel<BN>, grid, dim3(192), smem, stream, tmG, tmX, p));
   return 0;

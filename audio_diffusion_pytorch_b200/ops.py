@@ -14,8 +14,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import (ConvGemmArgs, NarrowConvArgs, NarrowConvBwdArgs, StemInArgs, StemInBwdArgs,
-                   StemOutArgs, StemOutBwdArgs, WgradArgs)
+from ._lib import (AttentionBwdArgs, ConvGemmArgs, NarrowConvArgs, NarrowConvBwdArgs, StemInArgs,
+                   StemInBwdArgs, StemOutArgs, StemOutBwdArgs, WgradArgs)
 
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 
@@ -205,13 +205,15 @@ def ln_film(x: Tensor, y: Tensor, scale_shift: Optional[Tensor] = None, ss_strid
     return y
 
 
-def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: float) -> Tensor:
-    """q: bf16 view [B, Tq, >=heads*64] (row pitch = stride(1)); k, v over Tk rows."""
+def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: float,
+              lse: Optional[Tensor] = None) -> Tensor:
+    """q: bf16 view [B, Tq, >=heads*64] (row pitch = stride(1)); k, v over Tk rows.
+    lse: optional fp32 [B, heads, Tq] output (kept for attention_bwd)."""
     B, Tq = q.shape[0], q.shape[1]
     Tk = k.shape[1]
     _launch(lambda: _lib.lib().adp_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                              B, heads, Tq, Tk, q.stride(1), k.stride(1),
-                                             v.stride(1), o.stride(1), scale, _stream()),
+                                             v.stride(1), o.stride(1), scale, _p(lse), _stream()),
             "adp_attention",
             lambda: (f"attention[B={B} H={heads} Tq={Tq} Tk={Tk}]", 4.0 * B * heads * Tq * Tk * 64,
                      (2 * B * Tq + 2 * B * Tk) * heads * 64 * 2))
@@ -363,11 +365,12 @@ def gn_bwd_apply(dxh: Tensor, x: Tensor, stats: Tensor, S: Tensor, dx: Tensor, g
 
 def ln_film_bwd(dy: Tensor, x: Tensor, scale_shift: Optional[Tensor], ss_stride: int, dx: Tensor, *,
                 dss: Optional[Tensor] = None, dss_stride: int = 0,
-                colsum: Optional[Tensor] = None, eps: float = 1e-6) -> Tensor:
+                colsum: Optional[Tensor] = None, dres: Optional[Tensor] = None,
+                eps: float = 1e-6) -> Tensor:
     B, T, Cc = x.shape
     _launch(lambda: _lib.lib().adp_ln_film_bwd(dy.data_ptr(), x.data_ptr(), _p(scale_shift),
                                                ss_stride, dx.data_ptr(), _p(dss), dss_stride,
-                                               _p(colsum), B, T, Cc, eps, _stream()),
+                                               _p(colsum), _p(dres), B, T, Cc, eps, _stream()),
             "adp_ln_film_bwd", lambda: (f"ln_film_bwd[M={B * T} C={Cc}]", 0, _nb(dy, x, dx)))
     return dx
 
@@ -428,8 +431,10 @@ def stem_out_bwd(dv: Tensor, h: Tensor, x: Tensor, w: Tensor, bias: Optional[Ten
                  gscale: Optional[Tensor] = None, append: Optional[Tensor] = None,
                  noise: Optional[Tensor] = None, alpha: Optional[Tensor] = None,
                  beta: Optional[Tensor] = None, w_adapt: Optional[Tensor] = None,
-                 dw_adapt: Optional[Tensor] = None, db_adapt: Optional[Tensor] = None) -> Tensor:
+                 dw_adapt: Optional[Tensor] = None, db_adapt: Optional[Tensor] = None,
+                 dxin: Optional[Tensor] = None) -> Tensor:
     a = StemOutBwdArgs()
+    a.dxin = _p(dxin)
     a.dv, a.gscale, a.h, a.x, a.append = dv.data_ptr(), _p(gscale), h.data_ptr(), x.data_ptr(), _p(append)
     a.noise, a.alpha, a.beta = _p(noise), _p(alpha), _p(beta)
     a.w, a.bias, a.w_adapt, a.gate = w.data_ptr(), _p(bias), _p(w_adapt), gate.data_ptr()
@@ -446,8 +451,10 @@ def stem_out_bwd(dv: Tensor, h: Tensor, x: Tensor, w: Tensor, bias: Optional[Ten
 
 def stem_in_bwd(dout: Tensor, x: Tensor, dw: Tensor, dbias: Tensor, f: int, *,
                 append: Optional[Tensor] = None, noise: Optional[Tensor] = None,
-                alpha: Optional[Tensor] = None, beta: Optional[Tensor] = None) -> None:
+                alpha: Optional[Tensor] = None, beta: Optional[Tensor] = None,
+                w: Optional[Tensor] = None, dxin: Optional[Tensor] = None) -> None:
     a = StemInBwdArgs()
+    a.w, a.dxin = _p(w), _p(dxin)
     a.dout, a.x, a.append = dout.data_ptr(), x.data_ptr(), _p(append)
     a.noise, a.alpha, a.beta = _p(noise), _p(alpha), _p(beta)
     a.dw, a.dbias = dw.data_ptr(), dbias.data_ptr()
@@ -456,3 +463,30 @@ def stem_in_bwd(dout: Tensor, x: Tensor, dw: Tensor, dbias: Tensor, f: int, *,
     a.c0, a.f = dout.shape[-1], f
     _launch(lambda: _lib.lib().adp_stem_in_bwd(C.byref(a), _stream()), "adp_stem_in_bwd",
             lambda: ("stem_in_bwd", 0, _nb(dout, x)))
+
+
+def attention_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, d_o: Tensor, lse: Tensor, delta: Tensor,
+                  dq: Tensor, dk: Tensor, dv: Tensor, heads: int, scale: float) -> None:
+    """Backward of `attention`; all bf16 views [B, T, >=heads*64], lse / delta fp32 [B, heads, Tq]."""
+    a = AttentionBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
+    a.lse, a.delta = lse.data_ptr(), delta.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.B, a.H, a.Tq, a.Tk = q.shape[0], heads, q.shape[1], k.shape[1]
+    a.ldq, a.ldk, a.ldv, a.ldo, a.lddo = q.stride(1), k.stride(1), v.stride(1), o.stride(1), d_o.stride(1)
+    a.lddq, a.lddk, a.lddv = dq.stride(1), dk.stride(1), dv.stride(1)
+    a.scale = scale
+    B, Tq, Tk = a.B, a.Tq, a.Tk
+    _launch(lambda: _lib.lib().adp_attention_bwd(C.byref(a), _stream()), "adp_attention_bwd",
+            lambda: (f"attention_bwd[B={B} H={heads} Tq={Tq} Tk={Tk}]", 14.0 * B * heads * Tq * Tk * 64,
+                     (4 * B * Tq + 4 * B * Tk) * heads * 64 * 2))
+
+
+def ln_fold_bwd(w: Tensor, g: Tensor, b: Tensor, dwf: Tensor, dbf: Tensor, dw: Tensor, dg: Tensor,
+                db: Tensor) -> None:
+    """Unfolds the gradient of a LayerNorm-affine-folded projection (see adp_ln_fold_bwd)."""
+    N, Cc = w.shape
+    _launch(lambda: _lib.lib().adp_ln_fold_bwd(w.data_ptr(), g.data_ptr(), b.data_ptr(), dwf.data_ptr(),
+                                               dwf.stride(0), dbf.data_ptr(), dw.data_ptr(),
+                                               dg.data_ptr(), db.data_ptr(), N, Cc, _stream()),
+            "adp_ln_fold_bwd", lambda: (f"ln_fold_bwd[N={N} C={Cc}]", 0, 3 * N * Cc * 4))

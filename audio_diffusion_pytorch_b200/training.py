@@ -1,22 +1,32 @@
-"""Training step of the hot path: VDiffusion loss + backward through the B200 U-Net
-(reference diffusion.py:82-95, `loss = model(x); loss.backward()`).
+"""Differentiable execution of the B200 U-Net: the training step of the hot path
+(reference diffusion.py:82-95, `loss = model(x); loss.backward()`) and the generic
+`v = net(x, sigma, ...)` with autograd support (custom `loss_fn` / `diffusion_t`,
+reference models.py:28,37 and tests/testcustomloss.py:28).
 
-`fused_v_loss` returns the same scalar as the reference (`F.mse_loss(net(x_noisy, sigma),
-v_target)`) as a tensor wired into autograd by ONE custom Function: its backward runs the
-hand-written backward program (data-gradient GEMMs = adp_conv_gemm with transposed weights,
-weight-gradient GEMMs = adp_wgrad, GroupNorm / LayerNorm-FiLM / stem backward kernels) and
-hands every parameter its fp32 gradient in PyTorch layout, so optimizers, gradient clipping
-and DistributedDataParallel (NCCL all-reduce of `.grad` buckets) work unchanged.
+Two entry points, ONE hand-written backward program:
 
-The forward noising (alpha*x + beta*noise) is fused into the first kernel and the MSE +
-dL/dv into the last one.  Only the 3 tiny time-embedding linears run as PyTorch ops (their
-autograd supplies d(features); [B,1024] matrices, < 0.1 % of the step).
+* `fused_v_loss`  -- `F.mse_loss(net(alpha*x + beta*noise, sigma), alpha*noise - beta*x)` with the
+  noising fused into the first kernel and the MSE + dL/dv into the last one.
+* `differentiable_forward` -- returns v wired into autograd; backward receives dL/dv.
 
-Scope: attention-free U-Nets.  A net with AttentionItems raises --
-attention backward is not built yet and nothing falls back silently.
+The backward program = data-gradient GEMMs (adp_conv_gemm on transposed packed weights),
+weight-gradient GEMMs (adp_wgrad), GroupNorm / LayerNorm-FiLM / stem backward kernels, and for
+AttentionItem / CrossAttentionItem the flash-attention backward (adp_attention_bwd) plus the
+LayerNorm-folded projection backward (adp_ln_fold_bwd).  Every parameter receives its fp32
+gradient in PyTorch layout, so optimizers, gradient clipping and DistributedDataParallel work
+unchanged; gradients w.r.t. `append_channels` (DiffusionVocoder's `to_flat`), `embedding` (the
+classifier-free-guidance mask embedding) and `x` flow back as well.
+
+Only the 3 tiny time-embedding linears run as PyTorch ops (their autograd supplies d(features);
+[B,1024] matrices, < 0.1 % of the step).
+
+One plan (static activation buffers + two CUDA graphs) exists per input shape: a second forward
+on the same shape before the first one's backward would overwrite the saved activations, so each
+forward stamps a generation number and a stale backward raises instead of returning the wrong
+gradients.
 """
 from math import pi
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn.functional as F
@@ -29,44 +39,54 @@ from .unet import B200UNet, LevelParams, _pad_to
 class _TrainPlan:
     def __init__(self):
         self.fwd: List = []
-        self.bwd: List = []          # appended in forward order, executed reversed
-        self.post: List = []         # runs after the reversed list (conditioning backward)
         self.graph_f = self.graph_b = None
         self.runs_f = self.runs_b = 0
+        self.generation = 0
 
 
 def _zeros(shape, dev, dtype=torch.float32):
     return torch.zeros(shape, device=dev, dtype=dtype)
 
 
-def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
-    assert not any(net.attentions) and not any(net.cross_attentions), \
-        "training through AttentionItems is not built yet (attention backward)"
+def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin: bool) -> _TrainPlan:
+    """mode 'loss': noising + MSE fused (VDiffusion); 'v': plain net forward, backward from dL/dv.
+    M = embedding tokens (0 without CrossAttentionItems)."""
     dev = net.net.down.weight.device
     P = net.packed()
     plan = _TrainPlan()
     G, Fm = net.groups, net.features
     levels = net.levels()
     bf16 = torch.bfloat16
+    loss_mode = mode == "loss"
+    heads = net.heads or 0
+    mid = heads * 64
+    att_scale = 64 ** -0.5
 
     def act(*shape):
         return torch.empty(*shape, dtype=bf16, device=dev)
 
     # ---- static I/O
+    cin = net.x_channels + net.append_channels
     plan.x = _zeros((B, net.x_channels, T), dev)
-    plan.noise = _zeros((B, net.x_channels, T), dev)
+    plan.noise = _zeros((B, net.x_channels, T), dev) if loss_mode else None
     plan.append = _zeros((B, net.append_channels, T), dev) if net.append_channels else None
-    plan.alpha, plan.beta = _zeros((B,), dev), _zeros((B,), dev)
+    plan.alpha = _zeros((B,), dev) if loss_mode else None
+    plan.beta = _zeros((B,), dev) if loss_mode else None
     plan.cond = _zeros((B, Fm), dev)                      # SiLU(features), fp32 master
     plan.cond_bf = torch.zeros(1, B, Fm, dtype=bf16, device=dev)
     plan.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
     plan.dv = _zeros((B, net.out_channels, T), dev)
+    plan.v = None if loss_mode else _zeros((B, net.out_channels, T), dev)
     plan.gscale = torch.ones(1, device=dev)
     plan.dcond = _zeros((B, Fm), dev)
+    plan.dxin = _zeros((B, cin, T), dev) if want_dxin else None
+    E = net.embedding_features
+    plan.embedding = torch.zeros(B, M, E, dtype=bf16, device=dev) if M else None
+    plan.demb = torch.zeros(B, M, E, dtype=bf16, device=dev) if M else None
 
     # ---- statistics + gradient arenas
     n_items = sum(len(lv.items_down) + len(lv.items_up) for lv in levels)
-    arena = torch.zeros(4 * n_items + 4 * len(levels) + 8, B, G, 2, dtype=torch.float64, device=dev)
+    arena = torch.zeros(6 * n_items + 4 * len(levels) + 8, B, G, 2, dtype=torch.float64, device=dev)
     slot = [0]
 
     def new_stats():
@@ -112,27 +132,124 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
     plan.fwd.append(lambda: ops.conv_gemm(plan.cond_bf, P["cond_w"], ss_all.view(1, B, -1), c_in=Fm,
                                           n_valid=ss_all.shape[1], bias=cond_bias))
 
+    # ---- cross-attention context: LayerNorm(embedding) once per forward (the per-item
+    # norm_context affines are folded into each item's to_kv weights)
+    en = den = None
+    if M:
+        en, den = act(B, M, E), torch.zeros(B, M, E, dtype=bf16, device=dev)
+        plan.fwd.append(lambda: ops.ln_film(plan.embedding, en, None, 0, None, G, net.ATT_LN_EPS))
+    delta_ws = [None]    # shared fp32 workspace of adp_attention_bwd, sized for the largest item
+
+    def delta_for(Tl: int) -> Tensor:
+        if delta_ws[0] is None or delta_ws[0].numel() < B * heads * Tl:
+            delta_ws[0] = _zeros((B * heads * Tl,), dev)
+        return delta_ws[0]
+
     def conv3_bwd(dy: Tensor, a_in: Tensor, gw: Tensor, da: Tensor, wd: Tensor, C: int):
         """dy: grad of the conv output; a_in: its input; writes da, accumulates dW (3 taps)."""
         for tap, off in enumerate((-1, 0, 1)):
             ops.wgrad(dy, a_in, gw[tap], n=C, k=C, off=off)
         ops.conv_gemm(dy, wd, da, c_in=C, n_valid=C, taps=(-1, 0, 1))
 
-    # ---- one chain of ResnetItem+ModulationItem
+    # ---- AttentionItem / CrossAttentionItem (a_unet): x + to_out(softmax(q k^T / 8) v)
+    def attention_block(x: Tensor, xn: Tensor, ap: Dict, am, cross: bool, Tl: int, C: int,
+                        out_stats: Optional[Tensor]):
+        """x: the item's input (residual); xn = LayerNorm(x) (affine folded into the projections).
+        Appends the forward launches; returns (y2, backward closure dy2 -> dx)."""
+        o, y2 = act(B, Tl, mid), act(B, Tl, C)
+        lse = _zeros((B, heads, Tl), dev)
+        delta_for(Tl)
+        wo = am.to_out.weight
+        wd_out = packed_dgrad(lambda: ops.pack_linear(wo.detach().t().contiguous()))
+        gw_out = grad_for(wo)
+        d_o, dxn, dx = act(B, Tl, mid), act(B, Tl, C), act(B, Tl, C)
+        g1, b1 = am.norm.weight, am.norm.bias
+        g2, b2 = am.norm_context.weight, am.norm_context.bias
+        dWq, dWkv = grad_for(am.to_q.weight), grad_for(am.to_kv.weight)
+        dg1, db1, dg2, db2 = grad_for(g1), grad_for(b1), grad_for(g2), grad_for(b2)
+        if not cross:
+            qkv, dqkv = act(B, Tl, 3 * mid), act(B, Tl, 3 * mid)
+            q, k, v = qkv[..., :mid], qkv[..., mid:2 * mid], qkv[..., 2 * mid:]
+            plan.fwd.append(lambda: ops.conv_gemm(xn, ap["w_qkv"], qkv, c_in=C, n_valid=3 * mid,
+                                                  bias=ap["b_qkv"]))
+            plan.fwd.append(lambda: ops.attention(q, k, v, o, heads, att_scale, lse=lse))
+
+            def make_wd():
+                wf = torch.cat([am.to_q.weight.detach().float() * g1.detach().float()[None, :],
+                                am.to_kv.weight.detach().float() * g2.detach().float()[None, :]], 0)
+                return ops.pack_linear(wf.t().contiguous())          # [C, 3*mid]
+            wd_qkv = packed_dgrad(make_wd)
+            gwf, dbf = gbuf((3 * mid, C)), gbuf((3 * mid,))
+
+            def bwd(dy2: Tensor) -> Tensor:
+                ops.conv_gemm(dy2, wd_out, d_o, c_in=C, n_valid=mid)
+                ops.wgrad(dy2, o, gw_out, n=C, k=mid)
+                ops.attention_bwd(q, k, v, o, d_o, lse, delta_ws[0], dqkv[..., :mid],
+                                  dqkv[..., mid:2 * mid], dqkv[..., 2 * mid:], heads, att_scale)
+                ops.conv_gemm(dqkv, wd_qkv, dxn, c_in=3 * mid, n_valid=C)
+                ops.wgrad(dqkv, xn, gwf, n=3 * mid, k=C)
+                ops.colsum(dqkv, dbf)
+                ops.ln_fold_bwd(am.to_q.weight, g1, b1, gwf[:mid], dbf[:mid], dWq, dg1, db1)
+                ops.ln_fold_bwd(am.to_kv.weight, g2, b2, gwf[mid:], dbf[mid:], dWkv, dg2, db2)
+                ops.ln_film_bwd(dxn, x, None, 0, dx, dres=dy2, eps=net.ATT_LN_EPS)
+                return dx
+        else:
+            q, kv = act(B, Tl, mid), act(B, M, 2 * mid)
+            dq, dkv = act(B, Tl, mid), act(B, M, 2 * mid)
+            plan.fwd.append(lambda: ops.conv_gemm(en, ap["w_kv"], kv, c_in=E, n_valid=2 * mid,
+                                                  bias=ap["b_kv"]))
+            plan.fwd.append(lambda: ops.conv_gemm(xn, ap["w_q"], q, c_in=C, n_valid=mid, bias=ap["b_q"]))
+            plan.fwd.append(lambda: ops.attention(q, kv[..., :mid], kv[..., mid:], o, heads, att_scale,
+                                                  lse=lse))
+            wd_q = packed_dgrad(lambda: ops.pack_linear(
+                (am.to_q.weight.detach().float() * g1.detach().float()[None, :]).t().contiguous()))
+            wd_kv = packed_dgrad(lambda: ops.pack_linear(
+                (am.to_kv.weight.detach().float() * g2.detach().float()[None, :]).t().contiguous()))
+            gwq, dbq = gbuf((mid, C)), gbuf((mid,))
+            gwkv, dbkv = gbuf((2 * mid, E)), gbuf((2 * mid,))
+
+            def bwd(dy2: Tensor) -> Tensor:
+                ops.conv_gemm(dy2, wd_out, d_o, c_in=C, n_valid=mid)
+                ops.wgrad(dy2, o, gw_out, n=C, k=mid)
+                ops.attention_bwd(q, kv[..., :mid], kv[..., mid:], o, d_o, lse, delta_ws[0], dq,
+                                  dkv[..., :mid], dkv[..., mid:], heads, att_scale)
+                ops.conv_gemm(dq, wd_q, dxn, c_in=mid, n_valid=C)
+                ops.wgrad(dq, xn, gwq, n=mid, k=C)
+                ops.colsum(dq, dbq)
+                # d LayerNorm(embedding), summed over the cross-attention items (in place)
+                ops.conv_gemm(dkv, wd_kv, den, c_in=2 * mid, n_valid=E, residual=den)
+                ops.wgrad(dkv, en, gwkv, n=2 * mid, k=E)
+                ops.colsum(dkv, dbkv)
+                ops.ln_fold_bwd(am.to_q.weight, g1, b1, gwq, dbq, dWq, dg1, db1)
+                ops.ln_fold_bwd(am.to_kv.weight, g2, b2, gwkv, dbkv, dWkv, dg2, db2)
+                ops.ln_film_bwd(dxn, x, None, 0, dx, dres=dy2, eps=net.ATT_LN_EPS)
+                return dx
+        plan.fwd.append(lambda: ops.conv_gemm(o, ap["w_out"], y2, c_in=mid, n_valid=C, residual=x,
+                                              stats=out_stats, groups=G))
+        return y2, bwd
+
+    # ---- one chain of [ResnetItem, ModulationItem, AttentionItem?, CrossAttentionItem?]
     def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], items_m, lv: LevelParams, Tl: int):
         C = lv.ch
         narrow = C == 8
+        bwds: List = []
         for ip, im in zip(items_p, items_m):
             r_ = im.resnet
             ss = ss_all[:, ip["ss_off"]:]
             dss = dss_all[:, ip["ss_off"]:]
-            h_stats, y_stats = new_stats(), new_stats()
+            has_att, has_cross = im.attention is not None, im.cross is not None
+            h_stats = new_stats()
+            y_stats = None if (has_att or has_cross) else new_stats()
             S1, S2 = new_stats(), new_stats()
             h, rr, y = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
+            xn_first = act(B, Tl, C) if (has_att or has_cross) else None
             dgn1 = (grad_for(r_.gn1.weight), grad_for(r_.gn1.bias))
             dgn2 = (grad_for(r_.gn2.weight), grad_for(r_.gn2.bias))
             db1, db2 = grad_for(r_.conv1.bias), grad_for(r_.conv2.bias)
             dr, dh, dx, dxh = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
+
+            def modulation_fwd(rr=rr, y=y, ss=ss, ys=y_stats, xn=xn_first):
+                ops.ln_film(rr, y, ss, ss_stride, ys, G, net.MOD_LN_EPS, y2=xn, eps2=net.ATT_LN_EPS)
             if narrow:
                 dw1, dw2 = grad_for(r_.conv1.weight), grad_for(r_.conv2.weight)
                 db_scratch = gbuf((C,))
@@ -140,8 +257,7 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
                     x, h, s, ip["gn1"][0], ip["gn1"][1], ip["w1"], ip["b1"], G, stats_out=hs))
                 plan.fwd.append(lambda x=x, h=h, rr=rr, hs=h_stats, ip=ip: ops.narrow_conv(
                     h, rr, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], ip["b2"], G, residual=x))
-                plan.fwd.append(lambda rr=rr, y=y, ss=ss, ys=y_stats: ops.ln_film(
-                    rr, y, ss, ss_stride, ys, G, net.MOD_LN_EPS))
+                plan.fwd.append(modulation_fwd)
 
                 def bwd(dy, x=x, h=h, rr=rr, ss=ss, dss=dss, xs=x_stats, hs=h_stats, ip=ip, dr=dr,
                         dh=dh, dx=dx, dxh=dxh, S1=S1, S2=S2, dgn1=dgn1, dgn2=dgn2, dw1=dw1, dw2=dw2,
@@ -167,8 +283,7 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
                     h, a2, hs, ip["gn2"][0], ip["gn2"][1], G, net.GN_EPS))
                 plan.fwd.append(lambda x=x, a2=a2, rr=rr, ip=ip: ops.conv_gemm(
                     a2, ip["w2"], rr, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
-                plan.fwd.append(lambda rr=rr, y=y, ss=ss, ys=y_stats: ops.ln_film(
-                    rr, y, ss, ss_stride, ys, G, net.MOD_LN_EPS))
+                plan.fwd.append(modulation_fwd)
                 da = act(B, Tl, C)
                 gw = {"w1": gbuf((3, C, C)), "w2": gbuf((3, C, C))}
 
@@ -189,13 +304,29 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
                     grads.__setitem__(id(r_.conv2.weight), gw["w2"].permute(1, 2, 0))))
             grads[id(im.modulation.proj.weight)] = ("cond_w", ip["ss_off"], 2 * C)
             grads[id(im.modulation.proj.bias)] = ("cond_b", ip["ss_off"], 2 * C)
-            plan.bwd.append(("item", bwd))
+            chain = [bwd]
             x, x_stats = y, y_stats
-        return x, x_stats
+            xn = xn_first
+            for kind, am in (("att", im.attention), ("cross", im.cross)):
+                if am is None:
+                    continue
+                last = kind == "cross" or not has_cross
+                ost = new_stats() if last else None
+                if xn is None:                       # second attention of the item: its own pre-norm
+                    xn = act(B, Tl, C)
+                    plan.fwd.append(lambda x=x, xn=xn: ops.ln_film(x, xn, None, 0, None, G, net.ATT_LN_EPS))
+                x, att_bwd = attention_block(x, xn, ip[kind], am, kind == "cross", Tl, C, ost)
+                x_stats, xn = ost, None
+                chain.append(att_bwd)
+
+            def item_bwd(dy, chain=chain):
+                for fn in reversed(chain):
+                    dy = fn(dy)
+                return dy
+            bwds.append(item_bwd)
+        return x, x_stats, bwds
 
     # ---- recursive level walk; returns (output tensor, its stats, backward closure)
-    tape: List = []   # executed in reverse: each entry is a callable(dy) -> dx
-
     def level(i: int, x_in: Optional[Tensor], T_in: int):
         lv, Lp = levels[i], P["levels"][i]
         Tl, C = T_in // lv.factor, lv.ch
@@ -216,18 +347,12 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
             gw_down = gbuf((C, kdim))
             finals.append(lambda: grads.__setitem__(
                 id(lv.down.weight), gw_down.view(C, lv.factor, lv.in_ch).permute(0, 2, 1)))
-        n_before = len(plan.bwd)
-        x, st = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl)
-        items_down_bwd = [b for _, b in plan.bwd[n_before:]]
-        del plan.bwd[n_before:]
+        x, st, items_down_bwd = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl)
         inner = None
         skip = x
         if not innermost:
             x, st, inner = level(i + 1, skip, Tl)
-        n_before = len(plan.bwd)
-        x, st = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl)
-        items_up_bwd = [b for _, b in plan.bwd[n_before:]]
-        del plan.bwd[n_before:]
+        x, st, items_up_bwd = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl)
         gate = ss_all[:, Lp["gate_off"]:]
         dgate = dss_all[:, Lp["gate_off"]:]
         grads[id(lv.merge.weight)] = ("cond_w", Lp["gate_off"], lv.out_ch)
@@ -244,13 +369,14 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
             plan.fwd.append(lambda: ops.stem_out(
                 x_last, plan.x, Lp["up_w"], Lp["up_b"], gate, lv.factor, append=plan.append,
                 w_adapt=Lp.get("adapt_w"), b_adapt=Lp.get("adapt_b"), noise=plan.noise,
-                alpha=plan.alpha, beta=plan.beta, loss_sum=plan.loss_sum, dv=plan.dv))
+                alpha=plan.alpha, beta=plan.beta, loss_sum=plan.loss_sum if loss_mode else None,
+                dv=plan.dv if loss_mode else None, v_out=plan.v))
 
             def backward_level0():
                 ops.stem_out_bwd(plan.dv, x_last, plan.x, Lp["up_w"], Lp["up_b"], gate, lv.factor, dh0,
                                  dw_up, db_up, dgate, gscale=plan.gscale, append=plan.append,
                                  noise=plan.noise, alpha=plan.alpha, beta=plan.beta,
-                                 w_adapt=Lp.get("adapt_w"), dw_adapt=dwa, db_adapt=dba)
+                                 w_adapt=Lp.get("adapt_w"), dw_adapt=dwa, db_adapt=dba, dxin=plan.dxin)
                 d = dh0
                 for b_ in reversed(items_up_bwd):
                     d = b_(d)
@@ -259,7 +385,8 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
                 for b_ in reversed(items_down_bwd):
                     d = b_(d)
                 ops.stem_in_bwd(d, plan.x, dw_down, db_down, lv.factor, append=plan.append,
-                                noise=plan.noise, alpha=plan.alpha, beta=plan.beta)
+                                noise=plan.noise, alpha=plan.alpha, beta=plan.beta,
+                                w=Lp["down_w"], dxin=plan.dxin)
             return None, None, backward_level0
 
         # levels >= 1: up conv writes y (pre-gate), skip_gate merges with the level's input
@@ -269,6 +396,7 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
         if f > 1:
             plan.fwd.append(lambda: ops.conv_gemm(x_last, Lp["up_w"], y_up.view(B, Tl, f * Co), c_in=C,
                                                   n_valid=Co, up_factor=f, bias=Lp["up_b"]))
+
             def make_wd_up():
                 w = lv.up.weight.detach().float()
                 w0, w1, w2 = w[:, :, 0], w[:, :, 1], w[:, :, 2]
@@ -340,29 +468,33 @@ def build_train_plan(net: B200UNet, B: int, T: int) -> _TrainPlan:
         return out, ost, backward_level
 
     _, _, backward0 = level(0, None, T)
-    plan.backward0 = backward0
+    assert slot[0] <= arena.shape[0]
     plan.flat = flat
     plan.refreshers, plan.version = refreshers, net._version()
     plan.grads, plan.finals = grads, finals
     plan.ss_all, plan.dss_all = ss_all, dss_all
     # conditioning projection backward
-    n_pad_rows = P["cond_w"].shape[0]
     plan.dw_all = _zeros((n_tot, Fm), dev)
     plan.dbias_all = _zeros((n_tot,), dev)
     plan.n_tot = n_tot
 
-    def cond_backward():
+    def backward_program():
+        flat.zero_()
+        if den is not None:
+            den.zero_()
+        backward0()
+        if den is not None:      # d embedding = LayerNorm backward of the summed context gradients
+            ops.ln_film_bwd(den, plan.embedding, None, 0, plan.demb, eps=net.ATT_LN_EPS)
         plan.dcond.zero_()
         ops.cond_bwd(dss_all, plan.cond_bf.view(B, Fm).float(), P["cond_w"], plan.dw_all,
                      plan.dbias_all, plan.dcond, n_tot)
-    plan.cond_backward = cond_backward
+    plan.backward_program = backward_program
     return plan
 
 
 def _run(plan: _TrainPlan, which: str, use_graph: bool) -> None:
     """Eager on the first call, captured on the second, replayed afterwards."""
-    prog = (lambda: [f() for f in plan.fwd]) if which == "f" else \
-        (lambda: (plan.flat.zero_(), plan.backward0(), plan.cond_backward()))
+    prog = (lambda: [f() for f in plan.fwd]) if which == "f" else plan.backward_program
     runs = plan.runs_f if which == "f" else plan.runs_b
     graph = plan.graph_f if which == "f" else plan.graph_b
     if not use_graph or runs == 0:
@@ -385,39 +517,61 @@ def _run(plan: _TrainPlan, which: str, use_graph: bool) -> None:
         plan.runs_b += 1
 
 
-class _UNetVLoss(torch.autograd.Function):
+class _UNetFn(torch.autograd.Function):
+    """mode 'loss' -> scalar MSE loss; mode 'v' -> v [B, out, T].  Inputs that may receive a
+    gradient: x, append, cond (SiLU of the time features), embedding, and every parameter."""
+
     @staticmethod
-    def forward(ctx, net: B200UNet, x, noise, sigmas, append, cond, *params):
+    def forward(ctx, net: B200UNet, mode: str, x, noise, sigmas, append, cond, embedding, *params):
         B, _, T = x.shape
-        key = ("train", B, T)
+        M = embedding.shape[1] if (embedding is not None and any(net.cross_attentions)) else 0
+        need = ctx.needs_input_grad       # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
+        want_dxin = bool(need[2] or need[5])
+        key = ("train", B, T, M, mode, want_dxin)
         net.packed()                         # in-place refresh of the forward packs
         plan = net._plans.get(key)
         if plan is None:
             ops.device_check()
-            plan = net._plans[key] = build_train_plan(net, B, T)
+            plan = net._plans[key] = build_train_plan(net, B, T, M, mode, want_dxin)
         elif plan.version != net._version():
             with torch.no_grad():
                 for r in plan.refreshers:
                     r()
             plan.version = net._version()
         plan.x.copy_(x)
-        plan.noise.copy_(noise)
         if net.append_channels:
             assert append is not None, "append_channels is required (AppendChannelsPlugin)"
             plan.append.copy_(append)
-        angle = sigmas.float() * pi / 2
-        plan.alpha.copy_(torch.cos(angle))
-        plan.beta.copy_(torch.sin(angle))
+        if mode == "loss":
+            plan.noise.copy_(noise)
+            angle = sigmas.float() * pi / 2
+            plan.alpha.copy_(torch.cos(angle))
+            plan.beta.copy_(torch.sin(angle))
+        if M:
+            plan.embedding.copy_(embedding)
         plan.cond.copy_(cond)
         _run(plan, "f", net.use_cuda_graph)
-        ctx.plan, ctx.net, ctx.n_params = plan, net, len(params)
+        plan.generation += 1
+        ctx.plan, ctx.net, ctx.mode, ctx.generation = plan, net, mode, plan.generation
         ctx.params = params
-        return (plan.loss_sum / plan.dv.numel()).float().reshape(())
+        ctx.has_emb = M > 0
+        ctx.x_dtype = x.dtype
+        if mode == "loss":
+            return (plan.loss_sum / plan.dv.numel()).float().reshape(())
+        return plan.v.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         plan, net = ctx.plan, ctx.net
-        plan.gscale.copy_(grad_out.reshape(1))
+        if plan.generation != ctx.generation:
+            raise RuntimeError(
+                "B200UNet: another forward ran on the same input shape before this backward; its "
+                "saved activations were overwritten (one static plan per shape).  Call backward() "
+                "before the next forward of that shape.")
+        if ctx.mode == "loss":
+            plan.gscale.copy_(grad_out.reshape(1))
+        else:
+            plan.dv.copy_(grad_out)
         _run(plan, "b", net.use_cuda_graph)
         for fin in plan.finals:
             fin()
@@ -427,22 +581,32 @@ class _UNetVLoss(torch.autograd.Function):
             if isinstance(g, tuple):
                 kind, off, n = g
                 g = plan.dw_all[off:off + n] if kind == "cond_w" else plan.dbias_all[off:off + n]
-            out.append(None if g is None else g.reshape(p.shape).to(p.dtype).contiguous())
-        return (None, None, None, None, None, plan.dcond.clone(), *out)
+            # clones: .grad must never alias the plan's arenas (they are rewritten next backward)
+            out.append(None if g is None else g.reshape(p.shape).to(p.dtype).clone())
+        dx = d_append = d_emb = None
+        need = ctx.needs_input_grad        # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
+        if plan.dxin is not None:
+            cx = net.x_channels
+            if need[2]:
+                dx = plan.dxin[:, :cx]
+                if ctx.mode == "loss":     # x enters through x_noisy (alpha) and the target (beta)
+                    a, b = plan.alpha.view(-1, 1, 1), plan.beta.view(-1, 1, 1)
+                    dx = a * dx + b * plan.dv * plan.gscale
+                dx = dx.to(ctx.x_dtype).clone()
+            if need[5] and net.append_channels:
+                d_append = plan.dxin[:, cx:].clone()
+        if ctx.has_emb and need[7]:
+            d_emb = plan.demb.float()
+        return (None, None, dx, None, None, d_append, plan.dcond.clone(), d_emb, *out)
 
 
-def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
-                 append_channels: Optional[Tensor] = None, features: Optional[Tensor] = None,
-                 **unsupported) -> Tensor:
-    """mse(net(alpha*x + beta*noise, sigma), alpha*noise - beta*x)  (reference diffusion.py:90-95)."""
-    assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
-    for k, v in unsupported.items():
-        assert v is None or k in ("embedding_scale", "embedding_mask_proba", "channels"), \
-            f"training with `{k}` is outside the built hot path"
-    # time features in PyTorch (autograd gives their gradients; three [B,1024] linears)
+def _time_cond(net: B200UNet, sigmas: Optional[Tensor], features: Optional[Tensor]) -> Tensor:
+    """SiLU(f), f = MLP(GELU(NumberEmbedder(sigma))) (+features): a_unet TimeConditioningPlugin, as
+    PyTorch ops so that autograd provides the gradients of its three [B,1024] linears."""
     if net.time is not None:
+        assert sigmas is not None, "time conditioning requires the time argument"
         t = net.time
-        s = sigmas.float().unsqueeze(-1)
+        s = sigmas.float().reshape(-1, 1)
         fr = s * t.weights * 2 * pi
         emb = t.to_out(torch.cat([s, fr.sin(), fr.cos()], dim=-1))
         f = F.gelu(t.mlp(F.gelu(t.mlp(F.gelu(emb)))))
@@ -451,7 +615,56 @@ def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
     else:
         assert features is not None, "use_time_conditioning=False needs features="
         f = features
-    cond = F.silu(f)
+    return F.silu(f)
+
+
+def _train_embedding(net: B200UNet, B: int, embedding: Optional[Tensor], embedding_scale: float,
+                     embedding_mask_proba: float) -> Optional[Tensor]:
+    """a_unet ClassifierFreeGuidancePlugin at training time: per-sample Bernoulli swap with the
+    learned mask embedding (PyTorch ops, so its gradient reaches `fixed_embedding`)."""
+    if net.use_embedding_cfg:
+        assert embedding is not None, "ClassiferFreeGuidancePlugin requires embedding"
+        if embedding_scale != 1.0:
+            raise NotImplementedError(
+                "embedding_scale != 1 under autograd (two guided evaluations with gradients) is "
+                "outside the built path; guidance is a sampling-time feature -- call under no_grad")
+        if embedding_mask_proba > 0.0:
+            fixed = net.fixed_embedding.weight[: embedding.shape[1]].unsqueeze(0).expand_as(embedding)
+            mask = torch.bernoulli(torch.full((B, 1, 1), float(embedding_mask_proba),
+                                              device=embedding.device)).to(torch.bool)
+            embedding = torch.where(mask, fixed, embedding)
+    if any(net.cross_attentions):
+        assert embedding is not None, "CrossAttentionItem requires embedding"
+        return embedding.float()
+    return None
+
+
+def _net_params(net: B200UNet):
     time_ids = {id(p) for p in (net.time.parameters() if net.time is not None else [])}
-    params = [p for p in net.parameters() if id(p) not in time_ids]
-    return _UNetVLoss.apply(net, x.float(), noise.float(), sigmas, append_channels, cond, *params)
+    fixed_ids = {id(p) for p in (net.fixed_embedding.parameters() if net.fixed_embedding is not None else [])}
+    return [p for p in net.parameters() if id(p) not in time_ids and id(p) not in fixed_ids]
+
+
+def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
+                 append_channels: Optional[Tensor] = None, features: Optional[Tensor] = None,
+                 embedding: Optional[Tensor] = None, embedding_scale: float = 1.0,
+                 embedding_mask_proba: float = 0.0, channels=None) -> Tensor:
+    """mse(net(alpha*x + beta*noise, sigma), alpha*noise - beta*x)  (reference diffusion.py:90-95)."""
+    assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+    assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
+    cond = _time_cond(net, sigmas, features)
+    emb = _train_embedding(net, x.shape[0], embedding, embedding_scale, embedding_mask_proba)
+    return _UNetFn.apply(net, "loss", x.float(), noise.float(), sigmas, append_channels, cond, emb,
+                         *_net_params(net))
+
+
+def differentiable_forward(net: B200UNet, x: Tensor, time: Optional[Tensor], *,
+                           features: Optional[Tensor] = None, embedding: Optional[Tensor] = None,
+                           embedding_scale: float = 1.0, embedding_mask_proba: float = 0.0,
+                           append_channels: Optional[Tensor] = None) -> Tensor:
+    """v = net(x, time, ...) with autograd support (custom loss_fn / diffusion_t)."""
+    assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+    cond = _time_cond(net, time, features)
+    emb = _train_embedding(net, x.shape[0], embedding, embedding_scale, embedding_mask_proba)
+    v = _UNetFn.apply(net, "v", x.float(), None, time, append_channels, cond, emb, *_net_params(net))
+    return v.to(x.dtype)

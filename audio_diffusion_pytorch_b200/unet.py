@@ -228,6 +228,8 @@ class B200UNet(nn.Module):
         self._plans: Dict[Tuple, _Plan] = {}
         self._packed = None
         self._packed_version = None
+        self._fingerprint = None
+        self._storage_sig = None
         self.use_cuda_graph = True
         # GroupNorm+SiLU applied inside the conv GEMM by transform warps (adp_conv_gemm gn_*).
         # Verified bit-compatible with the two-kernel path but measured SLOWER on the README
@@ -256,15 +258,55 @@ class B200UNet(nn.Module):
         for s, d in zip(src, dst):
             assert s.shape == d.shape, f"shape mismatch {tuple(s.shape)} vs {tuple(d.shape)}"
             d.copy_(s)
-        self._packed = None
 
     def _version(self) -> int:
         return sum(p._version for p in self.parameters())
+
+    def _storage_signature(self):
+        return tuple((p.data_ptr(), p.dtype) for p in self.parameters())
+
+    def invalidate(self) -> None:
+        """Drops every packed weight, plan and captured graph.  Needed after a parameter was
+        re-pointed (`p.data = ...`, `.to()`, `.half()`, `load_state_dict(assign=True)`); in-place
+        updates through the Parameter (optimizers, `load_state_dict`, `copy_`) are tracked by the
+        version counters and refresh the packs in place instead."""
+        self._plans.clear()
+        self._packed = None
+        self._packed_version = None
+        self._fingerprint = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_plans"):
+            self.invalidate()
+        return out
+
+    @torch.no_grad()
+    def _check_untracked_updates(self) -> None:
+        """`p.data.add_()` / `.data.copy_()` style updates (EMA wrappers, manual init, weight
+        clipping) bump no version counter.  Inference entry points therefore compare a cheap device
+        fingerprint of all parameters (one multi-tensor norm + one small device->host read per
+        call, outside the step loop) and re-pack when it moved."""
+        ps = [p for p in self.parameters()]
+        if not ps or not ps[0].is_cuda:
+            return
+        fp = torch.stack(torch._foreach_norm(ps)).double().cpu()
+        if self._fingerprint is not None and not torch.equal(fp, self._fingerprint):
+            self._packed_version = None          # force an in-place re-pack
+            for plan in self._plans.values():
+                if hasattr(plan, "version"):
+                    plan.version = None
+        self._fingerprint = fp
 
     @torch.no_grad()
     def packed(self):
         """Kernel-layout copies of the weights (bf16 GEMM operands, folded LayerNorm affines,
         one concatenated conditioning projection).  Rebuilt when a parameter changes."""
+        sig = self._storage_signature()
+        if getattr(self, "_storage_sig", None) != sig:   # a parameter was re-pointed: addresses
+            if getattr(self, "_storage_sig", None) is not None:   # baked into plans are stale
+                self.invalidate()
+            self._storage_sig = sig
         v = self._version()
         if self._packed is not None and self._packed_version == v:
             return self._packed
@@ -446,6 +488,9 @@ class B200UNet(nn.Module):
         plan.embedding = torch.zeros(Bh, M, self.embedding_features, dtype=torch.bfloat16,
                                      device=dev) if M else None
         plan.cfg_scale = None
+        plan.en = None                       # LayerNorm(embedding), shared by all cross-attentions
+        plan.pre = []                        # step-invariant launches of a sampling plan
+        add_ctx = plan.pre.append if mode == "sample" else plan.add
 
         # ---- statistics arena (zeroed once per forward)
         n_slots = 2 + sum(2 * (len(lv.items_down) + len(lv.items_up)) + 3 for lv in levels)
@@ -554,21 +599,22 @@ class B200UNet(nn.Module):
                             64 ** -0.5))
                         pool.put(qkv)
                     else:
+                        # context K/V do not depend on x or sigma: in sampling mode they are
+                        # projected ONCE per sample() call (plan.pre), not once per step
                         E = self.embedding_features
                         q = pool.get(Bh, Tl, mid)
-                        en = pool.get(Bh, M, E)
-                        kv = pool.get(Bh, M, 2 * mid)
-                        plan.add(lambda en=en: ops.ln_film(plan.embedding, en, None, 0, None, G,
-                                                           self.ATT_LN_EPS))
-                        plan.add(lambda en=en, kv=kv, ap=ap: ops.conv_gemm(
-                            en, ap["w_kv"], kv, c_in=E, n_valid=2 * mid, bias=ap["b_kv"]))
+                        if plan.en is None:
+                            plan.en = torch.empty(Bh, M, E, dtype=torch.bfloat16, device=dev)
+                            add_ctx(lambda: ops.ln_film(plan.embedding, plan.en, None, 0, None, G,
+                                                        self.ATT_LN_EPS))
+                        kv = torch.empty(Bh, M, 2 * mid, dtype=torch.bfloat16, device=dev)
+                        add_ctx(lambda kv=kv, ap=ap: ops.conv_gemm(
+                            plan.en, ap["w_kv"], kv, c_in=E, n_valid=2 * mid, bias=ap["b_kv"]))
                         plan.add(lambda xn=xn, q=q, ap=ap: ops.conv_gemm(
                             xn, ap["w_q"], q, c_in=C, n_valid=mid, bias=ap["b_q"]))
                         plan.add(lambda q=q, kv=kv, o=o: ops.attention(
                             q, kv[..., :mid], kv[..., mid:], o, self.heads, 64 ** -0.5))
                         pool.put(q)
-                        pool.put(en)
-                        pool.put(kv)
                     plan.add(lambda o=o, y2=y2, x=x, ap=ap, os_=out_stats: ops.conv_gemm(
                         o, ap["w_out"], y2, c_in=mid, n_valid=C, residual=x, stats=os_, groups=G))
                     pool.put(xn)
@@ -728,17 +774,30 @@ class B200UNet(nn.Module):
         M = embedding.shape[1] if (exists(embedding) and any(self.cross_attentions)) else 0
         return B, T, (2 * B if cfg else B), M
 
-    @torch.no_grad()
     def forward(self, x: Tensor, time: Optional[Tensor] = None, *, features: Optional[Tensor] = None,
                 embedding: Optional[Tensor] = None, embedding_scale: float = 1.0,
                 embedding_mask_proba: float = 0.0, channels=None,
                 append_channels: Optional[Tensor] = None) -> Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            pass  # training goes through VDiffusion (fused loss + backward); plain forward is inference
         assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
         assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
         if self.use_embedding_cfg:
             assert exists(embedding), "ClassiferFreeGuidancePlugin requires embedding"
+        if torch.is_grad_enabled() and (
+                any(p.requires_grad for p in self.parameters()) or
+                any(exists(t) and t.requires_grad for t in (x, features, embedding, append_channels))):
+            # differentiable: custom loss_fn / diffusion_t (reference models.py:28,37)
+            from .training import differentiable_forward
+            return differentiable_forward(self, x, time, features=features, embedding=embedding,
+                                          embedding_scale=embedding_scale,
+                                          embedding_mask_proba=embedding_mask_proba,
+                                          append_channels=append_channels)
+        return self._forward_inference(x, time, features, embedding, embedding_scale,
+                                       embedding_mask_proba, append_channels)
+
+    @torch.no_grad()
+    def _forward_inference(self, x, time, features, embedding, embedding_scale,
+                           embedding_mask_proba, append_channels) -> Tensor:
+        self._check_untracked_updates()
         B, T, Bh, M = self._shape_key(x, embedding, embedding_scale)
         plan = self._plan(B, T, Bh, M, "v", (float(embedding_scale) if Bh != B else None,
                                              exists(features)))
@@ -753,6 +812,7 @@ class B200UNet(nn.Module):
         """VSampler's loop (reference diffusion.py:183-188) with the per-step update fused into
         the net's last kernel: one graph launch per step, no host sync inside the loop."""
         assert x_noisy.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+        self._check_untracked_updates()
         embedding = kwargs.get("embedding")
         scale = kwargs.get("embedding_scale", 1.0)
         B, T, Bh, M = self._shape_key(x_noisy, embedding, scale)
@@ -760,6 +820,8 @@ class B200UNet(nn.Module):
                                                   exists(kwargs.get("features"))))
         self._stage_inputs(plan, x_noisy.float(), sigmas[0], kwargs.get("features"), embedding, scale,
                            kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"))
+        for fn in plan.pre:          # cross-attention context K/V: once per call
+            fn()
         num_steps = sigmas.shape[0] - 1
         ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], dim=1).float().contiguous()
         sig = sigmas.float().repeat(1, Bh // B).contiguous()      # [N+1, Bh]

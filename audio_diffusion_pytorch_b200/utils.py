@@ -3,6 +3,7 @@ windowed-sinc resampler behind DiffusionUpsampler (one strided convolution per c
 the step loop; its filter bank is built once per (factors, dtype, device) and cached), and the
 CPU-generator noise draw.  Behavioural spec: reference utils.py:17-125."""
 import functools
+import inspect
 import math
 from typing import Any, Callable, Dict, Optional, Tuple, Union
 
@@ -16,11 +17,12 @@ def exists(val: Any) -> bool:
 
 
 def default(val: Any, fallback: Union[Any, Callable[[], Any]]) -> Any:
-    """`val` unless it is None; a callable fallback (not a class) is evaluated lazily."""
+    """`val` unless it is None; a plain-function fallback (def / lambda) is evaluated lazily,
+    any other object -- including callables such as nn.Module instances -- is returned as is
+    (reference utils.py:27-30, `inspect.isfunction`)."""
     if val is not None:
         return val
-    lazy = callable(fallback) and not isinstance(fallback, type)
-    return fallback() if lazy else fallback
+    return fallback() if inspect.isfunction(fallback) else fallback
 
 
 def groupby(prefix: str, d: Dict[str, Any], keep_prefix: bool = False) -> Tuple[Dict, Dict]:

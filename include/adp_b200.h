@@ -111,10 +111,12 @@ int adp_ln_film_dual(const void* x, void* y, void* y2, const float* scale_shift,
 
 /* o = softmax(q k^T * scale) v per (batch, head), head dim 64 -- a_unet AttentionBase.
  * q: bf16 [B][Tq][ldq] (head h at columns [h*64,(h+1)*64)), k/v likewise over Tk rows,
- * o: bf16 [B][Tq][ldo].  tcgen05 flash attention (S and O accumulators in TMEM). */
+ * o: bf16 [B][Tq][ldo].  tcgen05 flash attention (S and O accumulators in TMEM).
+ * lse: optional fp32 [B][H][Tq] = log sum_k exp(scale * q.k) per row (kept by the training
+ * forward for adp_attention_bwd), or NULL. */
 int adp_attention(const void* q, const void* k, const void* v, void* o, int32_t B, int32_t H,
                   int32_t Tq, int32_t Tk, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo,
-                  float scale, adp_stream_t stream);
+                  float scale, float* lse, adp_stream_t stream);
 
 /* y[b][n] = out_act( sum_k in_act(x[b][k]) * w[n][k] + bias[n] ),  B <= 64 rows.
  * The step-conditioning linears: NumberEmbedder.to_out, TimeConditioningPlugin MLP,
@@ -250,10 +252,12 @@ int adp_gn_silu_bwd(const void* da, const void* x, const double* stats, const fl
 int adp_gn_bwd_apply(const void* dxh, const void* x, const double* stats, const double* S,
                      const void* dres, void* dx, float* colsum, int32_t B, int32_t T, int32_t C,
                      int32_t groups, float eps, adp_stream_t stream);
-/* Modulation backward: dx, dss[b][0:C] += sum_t dy*xhat, dss[b][C:2C] += sum_t dy. */
+/* Modulation backward: dx, dss[b][0:C] += sum_t dy*xhat, dss[b][C:2C] += sum_t dy.
+ * scale_shift == NULL: backward of the affine-free attention pre-norm; dres (bf16, optional) is a
+ * gradient arriving on a parallel path (the attention's residual), added to dx. */
 int adp_ln_film_bwd(const void* dy, const void* x, const float* scale_shift, int32_t ss_stride,
-                    void* dx, float* dss, int32_t dss_stride, float* colsum, int32_t B, int32_t T,
-                    int32_t C, float eps, adp_stream_t stream);
+                    void* dx, float* dss, int32_t dss_stride, float* colsum, const void* dres,
+                    int32_t B, int32_t T, int32_t C, float eps, adp_stream_t stream);
 /* out[c] += sum_{b,t} x[b][t][c] * (gate ? gate[b][c] : 1)   (bias gradients) */
 int adp_colsum(const void* x, const float* gate, int32_t ld_gate, float* out, int32_t B, int32_t T,
                int32_t C, adp_stream_t stream);
@@ -270,6 +274,33 @@ int adp_skip_gate_bwd(const void* dout, const void* y, const float* gate, int32_
  * dw[n][k] = sum_b dss[b][n]*cond[b][k]; dbias[n] = sum_b dss[b][n]; dcond += dss W. */
 int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond, const void* w, float* dw,
                  float* dbias, float* dcond, int32_t B, int32_t N, int32_t K, adp_stream_t stream);
+
+/* Backward of adp_attention (torch.autograd through a_unet AttentionBase in the reference):
+ * recomputes P = exp(scale*q k^T - lse) tile by tile.  dq like q, dk / dv like k / v.
+ * delta: fp32 [B][H][Tq] workspace (rowsum(dO o O), written by the call). */
+typedef struct adp_attention_bwd_args {
+  const void* q;        /* bf16 [B][Tq][ldq], head h at columns [h*64,(h+1)*64) */
+  const void* k;        /* bf16 [B][Tk][ldk] */
+  const void* v;        /* bf16 [B][Tk][ldv] */
+  const void* o;        /* bf16 [B][Tq][ldo]   forward output        */
+  const void* d_o;      /* bf16 [B][Tq][lddo]  gradient of o         */
+  const float* lse;     /* fp32 [B][H][Tq]     from adp_attention    */
+  float* delta;         /* fp32 [B][H][Tq]     workspace             */
+  void* dq;             /* bf16 [B][Tq][lddq] */
+  void* dk;             /* bf16 [B][Tk][lddk] */
+  void* dv;             /* bf16 [B][Tk][lddv] */
+  int32_t B, H, Tq, Tk;
+  int32_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  float scale;
+} adp_attention_bwd_args;
+int adp_attention_bwd(const adp_attention_bwd_args* args, adp_stream_t stream);
+
+/* The attention projections run with their LayerNorm affine folded in (Wf = W diag(g),
+ * bf = W b).  Unfolds the gradients: dw[N][C] = dwf*g + dbf (x) b (stored); dg[C] += colsum(dwf o W);
+ * db[C] += W^T dbf.  w, dw dense fp32 [N][C]; dwf fp32 [N][ldwf]. */
+int adp_ln_fold_bwd(const float* w, const float* g, const float* b, const float* dwf, int32_t ldwf,
+                    const float* dbf, float* dw, float* dg, float* db, int32_t N, int32_t C,
+                    adp_stream_t stream);
 
 typedef struct adp_narrow_conv_bwd_args {
   const void* dy;           /* bf16 [B][T][C] gradient of the conv output        */
@@ -308,6 +339,8 @@ typedef struct adp_stem_out_bwd_args {
   float* dgate;             /* fp32 [B][ld_dgate]                                 */
   float* dw_adapt;
   float* db_adapt;
+  float* dxin;              /* optional fp32 [B][cx+ca][T]: gradient w.r.t. cat([x, append]) through
+                               the skip path (identity or SkipAdapter), STORED (not accumulated) */
   int32_t B, T, cx, ca, c0, co, f, ld_gate, ld_dgate;
 } adp_stem_out_bwd_args;
 int adp_stem_out_bwd(const adp_stem_out_bwd_args* args, adp_stream_t stream);
@@ -321,6 +354,10 @@ typedef struct adp_stem_in_bwd_args {
   const float* beta;
   float* dw;                /* fp32 [c0][cx+ca][f]                                */
   float* dbias;             /* fp32 [c0]                                          */
+  const float* w;           /* fp32 [c0][cx+ca][f] (needed for dxin) or NULL      */
+  float* dxin;              /* optional fp32 [B][cx+ca][T]: += gradient w.r.t. cat([x, append])
+                               (the DiffusionVocoder trains `to_flat` through append_channels,
+                               reference models.py:203-209); run after adp_stem_out_bwd */
   int32_t B, T, cx, ca, c0, f;
 } adp_stem_in_bwd_args;
 int adp_stem_in_bwd(const adp_stem_in_bwd_args* args, adp_stream_t stream);

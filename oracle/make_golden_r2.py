@@ -1,0 +1,129 @@
+"""ORACLE / TEST INFRASTRUCTURE.  Run in the BUILD container only (needs /root/reference):
+
+    python oracle/make_golden_r2.py
+
+Golden vectors at the BASELINE.json configurations, produced by the UNMODIFIED reference package
+(`/root/reference/audio_diffusion_pytorch`) on the `oracle/a_unet` shim -- the cases the round-1
+review asked for: the README network at full size [1,2,2^18] (forward + 10-step VSampler), a
+50-step VSampler run (the headline metric is a 50-step sample), and the text-conditional /
+classifier-free-guidance network at README scale (cross_attentions=[0,0,0,1,1,1,1,1,1],
+embedding [B,64,768], scale 5.0).  Full-size tensors are committed as WINDOWS (16 windows of 1024
+samples spread over the clip) to keep the fixtures small; inputs are regenerated from their seeds
+by the tests.  Each case first re-proves port == reference on that configuration.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, "/root/reference")
+
+import audio_diffusion_pytorch as ref  # noqa: E402
+
+import reference_port as port  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+README = dict(in_channels=2, channels=[8, 32, 64, 128, 256, 512, 512, 1024, 1024],
+              factors=[1, 4, 4, 4, 2, 2, 2, 2, 2], items=[1, 2, 2, 2, 2, 2, 2, 4, 4],
+              attentions=[0, 0, 0, 0, 0, 1, 1, 1, 1], attention_heads=8, attention_features=64)
+CFG3 = dict(README, cross_attentions=[0, 0, 0, 1, 1, 1, 1, 1, 1], use_embedding_cfg=True,
+            embedding_max_length=64, embedding_features=768)
+TINY = dict(in_channels=2, channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2],
+            attentions=[0, 0, 1], attention_heads=2, attention_features=64)
+N_WIN, WIN = 16, 1024
+
+
+def windows(t: torch.Tensor) -> np.ndarray:
+    """[B, C, T] -> [B, C, N_WIN, WIN]: evenly spaced windows (first at 0, last ends at T)."""
+    T = t.shape[-1]
+    starts = [round(i * (T - WIN) / (N_WIN - 1)) for i in range(N_WIN)]
+    return np.stack([t[..., s:s + WIN].numpy() for s in starts], axis=-2), np.array(starts)
+
+
+def same(a, b, what):
+    assert torch.equal(a, b), f"port != reference for {what}: max diff {(a - b).abs().max()}"
+    print(f"  port == reference (bit-exact): {what}")
+
+
+def fingerprint(module):
+    ps = [p.detach().double() for p in module.parameters()]
+    return np.array([sum(float(p.sum()) for p in ps), sum(float(p.abs().sum()) for p in ps),
+                     float(sum(p.numel() for p in ps))])
+
+
+def build(cfg):
+    torch.manual_seed(0)
+    m_ref = ref.DiffusionModel(net_t=ref.UNetV0, diffusion_t=ref.VDiffusion, sampler_t=ref.VSampler, **cfg)
+    torch.manual_seed(0)
+    m_port = port.DiffusionModelPort(**cfg)
+    same(torch.cat([p.flatten() for p in m_ref.parameters()]),
+         torch.cat([p.flatten() for p in m_port.parameters()]), "same-seed construction")
+    return m_ref, m_port
+
+
+def case_tiny_50_steps():
+    m_ref, m_port = build(TINY)
+    g = torch.Generator().manual_seed(20)
+    noise = torch.randn(2, 2, 4096, generator=g)
+    s_ref = m_ref.sample(noise, num_steps=50)
+    same(m_port.sample(noise, num_steps=50), s_ref, "VSampler 50 steps (tiny)")
+    np.savez_compressed(os.path.join(OUT, "tiny_sample50.npz"), sample50=s_ref.numpy(),
+                        param_fingerprint=fingerprint(m_port), noise_seed=20)
+
+
+def case_readme_full_size():
+    m_ref, m_port = build(README)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(1, 2, 2 ** 18, generator=g)
+    sig = torch.tensor([0.37])
+    small = x[..., :2 ** 13].contiguous()
+    with torch.no_grad():
+        same(m_port.net(small, sig), m_ref.net(small, sig), "README net (2^13 clip)")
+        t0 = time.time()
+        v = m_ref.net(x, sig)
+        print(f"  full-size forward: {time.time() - t0:.1f} s")
+        t0 = time.time()
+        s10 = m_ref.sample(x, num_steps=10)
+        print(f"  full-size 10-step sample: {time.time() - t0:.1f} s")
+    v_w, starts = windows(v)
+    s_w, _ = windows(s10)
+    np.savez_compressed(os.path.join(OUT, "readme_full_size.npz"), sigma=sig.numpy(), v_windows=v_w,
+                        sample10_windows=s_w, starts=starts, param_fingerprint=fingerprint(m_port),
+                        x_seed=21, v_norm=float(v.norm()), branch_norm=float((v - x).norm()),
+                        sample10_norm=float(s10.norm()))
+
+
+def case_cfg3_readme_scale():
+    m_ref, m_port = build(CFG3)
+    g = torch.Generator().manual_seed(22)
+    T = 2 ** 15
+    x = torch.randn(1, 2, T, generator=g)
+    emb = torch.randn(1, 64, 768, generator=g)
+    sig = torch.tensor([0.61])
+    with torch.no_grad():
+        small = x[..., :2 ** 13].contiguous()
+        same(m_port.net(small, sig, embedding=emb, embedding_scale=5.0),
+             m_ref.net(small, sig, embedding=emb, embedding_scale=5.0), "cfg3 net, CFG 5 (2^13 clip)")
+        v1 = m_ref.net(x, sig, embedding=emb)
+        v5 = m_ref.net(x, sig, embedding=emb, embedding_scale=5.0)
+        s3 = m_ref.sample(x, num_steps=3, embedding=emb, embedding_scale=5.0)
+    np.savez_compressed(os.path.join(OUT, "cfg3_readme_scale.npz"), sigma=sig.numpy(),
+                        v_scale1=v1.numpy(), v_scale5=v5.numpy(), sample3=s3.numpy(),
+                        param_fingerprint=fingerprint(m_port), seed=22, length=T)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    only = sys.argv[1:]
+    for case in (case_tiny_50_steps, case_cfg3_readme_scale, case_readme_full_size):
+        if only and case.__name__ not in only:
+            continue
+        print(case.__name__)
+        case()
+    print("golden vectors written to", OUT)

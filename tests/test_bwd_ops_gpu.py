@@ -222,3 +222,100 @@ def test_stem_backward(ops, cx, ca, co, c0, f):
     ops.stem_in_bwd(dout, x, dwi, dbi, f, append=app, noise=noise, alpha=alpha, beta=beta)
     close(dwi, w_in.grad, 1e-3, 1e-3, "stem_in_bwd dw")
     close(dbi, b_in.grad, 1e-3, 1e-3, "stem_in_bwd dbias")
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk", [(2, 8, 256, 256), (1, 2, 128, 128), (2, 4, 200, 200),
+                                       (2, 8, 512, 64), (1, 2, 300, 8), (1, 1, 64, 384),
+                                       (1, 8, 1024, 1024)])
+def test_attention_bwd(ops, B, H, Tq, Tk):
+    """adp_attention (with its log-sum-exp output) + adp_attention_bwd against autograd through
+    F.scaled_dot_product_attention on the same bf16 q/k/v, read out of packed projection rows."""
+    mid = H * 64
+    if Tq == Tk:
+        qkv = bf(rnd(B, Tq, 3 * mid, seed=70))
+        q, k, v = qkv[..., :mid], qkv[..., mid:2 * mid], qkv[..., 2 * mid:]
+        dqkv = torch.full_like(qkv, float("nan"))
+        dq, dk, dv = dqkv[..., :mid], dqkv[..., mid:2 * mid], dqkv[..., 2 * mid:]
+    else:
+        q = bf(rnd(B, Tq, mid, seed=71))
+        kv = bf(rnd(B, Tk, 2 * mid, seed=72))
+        k, v = kv[..., :mid], kv[..., mid:]
+        dq = torch.full_like(q, float("nan"))
+        dkv = torch.full_like(kv, float("nan"))
+        dk, dv = dkv[..., :mid], dkv[..., mid:]
+    d_o = bf(rnd(B, Tq, mid, seed=73))
+    o = torch.empty(B, Tq, mid, dtype=torch.bfloat16, device=DEV)
+    lse = torch.full((B, H, Tq), float("nan"), device=DEV)
+    delta = torch.empty(B, H, Tq, device=DEV)
+    ops.attention(q, k, v, o, H, 64 ** -0.5, lse=lse)
+    ops.attention_bwd(q, k, v, o, d_o, lse, delta, dq, dk, dv, H, 64 ** -0.5)
+
+    def heads(t):
+        return t.float().reshape(B, -1, H, 64).transpose(1, 2)
+    qf, kf, vf = (heads(t).detach().requires_grad_(True) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf)
+    ref.backward(heads(d_o))
+    lse_ref = torch.logsumexp(qf.detach() @ kf.detach().transpose(-1, -2) * 64 ** -0.5, dim=-1)
+    close(lse, lse_ref, 1e-3, 1e-3, "lse")
+
+    def flat(t):
+        return t.transpose(1, 2).reshape(B, -1, mid)
+    close(dq, flat(qf.grad), 2 ** -6, 1.5e-2, f"dq B{B} H{H} Tq{Tq} Tk{Tk}")
+    close(dk, flat(kf.grad), 2 ** -6, 1.5e-2, "dk")
+    close(dv, flat(vf.grad), 2 ** -6, 1.5e-2, "dv")
+
+
+@pytest.mark.parametrize("N,C", [(128, 64), (1536, 512), (256, 768), (1024, 1024)])
+def test_ln_fold_bwd(ops, N, C):
+    w, g, b = rnd(N, C, seed=80), rnd(C, seed=81) * 0.3 + 1.0, rnd(C, seed=82) * 0.3
+    dwf, dbf = rnd(N, C, seed=83), rnd(N, seed=84)
+    dw = torch.full((N, C), float("nan"), device=DEV)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ops.ln_fold_bwd(w, g, b, dwf, dbf, dw, dg, db)
+    wr, gr, br = (t.double().detach().requires_grad_(True) for t in (w, g, b))
+    ((wr * gr[None, :]) * dwf.double()).sum().backward(retain_graph=True)
+    ((wr @ br) * dbf.double()).sum().backward()
+    close(dw, wr.grad, 1e-5, 1e-5, "dW")
+    close(dg, gr.grad, 1e-4, 1e-4, "dg")
+    close(db, br.grad, 1e-4, 1e-4, "db")
+
+
+def test_ln_bwd_with_residual_gradient(ops):
+    """Affine-free LayerNorm backward + a gradient arriving on the residual path (attention)."""
+    B, T, C = 2, 300, 256
+    x, dy, dres = bf(rnd(B, T, C, seed=90)), bf(rnd(B, T, C, seed=91)), bf(rnd(B, T, C, seed=92))
+    dx = torch.empty_like(x)
+    ops.ln_film_bwd(dy, x, None, 0, dx, dres=dres, eps=1e-5)
+    xr = x.float().requires_grad_(True)
+    F.layer_norm(xr, (C,), eps=1e-5).backward(dy.float())
+    close(dx, xr.grad + dres.float(), 2 ** -7, 1e-2, "ln bwd + dres")
+
+
+@pytest.mark.parametrize("adapter", [False, True])
+def test_stem_input_gradient(ops, adapter):
+    """dxin of adp_stem_out_bwd (skip path, stored) + adp_stem_in_bwd (DownsampleItem path, added)
+    against autograd of the same two ops."""
+    B, T, f, c0 = 2, 1024, 1, 8
+    cx, ca, co = (2, 2, 2) if adapter else (2, 0, 2)
+    cin = cx + ca
+    x, app = rnd(B, cx, T, seed=100), (rnd(B, ca, T, seed=101) if ca else None)
+    w_dn, b_dn = rnd(c0, cin, f, seed=102) * 0.5, rnd(c0, seed=103)
+    w_up, b_up = rnd(co, c0, 3, seed=104) * 0.3, rnd(co, seed=105)
+    w_ad = rnd(co, cin, seed=106) * 0.5 if adapter else None
+    b_ad = rnd(co, seed=107) if adapter else None
+    gate = rnd(B, 8, seed=108)
+    h = bf(rnd(B, T // f, c0, seed=109))
+    dv = rnd(B, co, T, seed=110)
+    dout = bf(rnd(B, T // f, c0, seed=111))
+    dxin = torch.full((B, cin, T), float("nan"), device=DEV)
+    dh = torch.empty_like(h)
+    z = lambda *s: torch.zeros(*s, device=DEV)  # noqa: E731
+    ops.stem_out_bwd(dv, h, x, w_up, b_up, gate, f, dh, z(co, c0, 3), z(co), z(B, 8), append=app,
+                     w_adapt=w_ad, dw_adapt=z(co, cin) if adapter else None,
+                     db_adapt=z(co) if adapter else None, dxin=dxin)
+    ops.stem_in_bwd(dout, x, z(c0, cin, f), z(c0), f, append=app, w=w_dn, dxin=dxin)
+    xin = (torch.cat([x, app], 1) if ca else x).detach().requires_grad_(True)
+    skip = F.conv1d(xin, w_ad[:, :, None], b_ad) if adapter else xin
+    down = F.conv1d(xin, w_dn, b_dn, stride=f)                      # [B, c0, T/f]
+    ((skip * dv).sum() + (down * dout.float().transpose(1, 2)).sum()).backward()
+    close(dxin, xin.grad, 1e-4, 1e-4, "dxin")

@@ -1,7 +1,11 @@
 """Training step parity: fused VDiffusion loss + hand-written backward of the B200 U-Net against
-torch.autograd through the CPU oracle (same weights, same x / noise / sigma).  Attention-free
-configs (BASELINE cfg4/cfg5 shape).  bf16 storage: loss within 2e-3 relative, every parameter
-gradient within 6e-2 rel-L2 (and the global gradient direction within 1e-3 cosine distance)."""
+torch.autograd through the CPU oracle (same weights, same x / noise / sigma): attention-free
+nets (BASELINE cfg4/cfg5 shape), nets with AttentionItem / CrossAttentionItem (README config,
+cfg3), the 9-level shape, custom loss functions through the differentiable net forward, the
+DiffusionVocoder front-end gradient, and the autograd contracts (accumulation, stale plans).
+bf16 storage: loss within 2e-3 relative; every parameter gradient within GRAD_TOL rel-L2 of the
+fp32 oracle gradient (floored at 10 % of the median gradient norm for analytically-zero
+gradients) and the global gradient direction within 1e-3 cosine distance."""
 import math
 
 import pytest
@@ -11,6 +15,10 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 CFG = dict(in_channels=2, channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+ATT = dict(CFG, attentions=[0, 0, 1], attention_heads=2, attention_features=64)
+TEXT = dict(ATT, cross_attentions=[0, 1, 1], use_embedding_cfg=True, embedding_max_length=8,
+            embedding_features=32)
+GRAD_TOL = 6e-2
 
 
 def oracle_loss(ref_net, x, noise, sigma, **kw):
@@ -29,7 +37,7 @@ def compare_grads(ref_params, got_params):
         rel = float((g - g_ref).norm() / g_ref.norm().clamp_min(floor))
         worst = max(worst, rel)
         dots += float((g * g_ref).sum()); n1 += float((g * g).sum()); n2 += float((g_ref * g_ref).sum())
-        if rel > 6e-2:
+        if rel > GRAD_TOL:
             print(f"  {name:60s} shape {tuple(p.shape)} rel-L2 {rel:.3e}")
     cos = dots / math.sqrt(n1 * n2)
     print(f"worst per-parameter rel-L2 {worst:.3e}; global cosine {cos:.6f}")
@@ -67,7 +75,7 @@ def test_loss_and_gradients_match_oracle(oracle_port, upsampler):
         print(f"call {call}: loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
         assert rel < 2e-3
         worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
-        assert worst < 6e-2 and cos > 1 - 1e-3
+        assert worst < GRAD_TOL and cos > 1 - 1e-3
 
 
 def test_optimizer_step_refreshes_packed_weights(oracle_port):
@@ -108,3 +116,229 @@ def test_model_forward_is_the_reference_call(oracle_port):
     loss.backward()
     assert loss.ndim == 0 and torch.isfinite(loss)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def _pair(oracle_port, adp, cfg):
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**cfg)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    return ref, model
+
+
+@pytest.mark.parametrize("case", ["self_attention", "cross_attention", "cross_attention_all_masked"])
+def test_attention_gradients_match_oracle(oracle_port, case):
+    """AttentionItem / CrossAttentionItem backward (adp_attention_bwd + LayerNorm-folded projection
+    backward): `loss = model(x); loss.backward()` on nets WITH attention (README.md:37-38)."""
+    import audio_diffusion_pytorch_b200 as adp
+    from audio_diffusion_pytorch_b200.training import fused_v_loss
+    cfg = ATT if case == "self_attention" else TEXT
+    ref, model = _pair(oracle_port, adp, cfg)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 2, 4096, generator=g)
+    noise = torch.randn(2, 2, 4096, generator=g)
+    sigma = torch.rand(2, generator=g)
+    kw_ref, kw = {}, {}
+    if case != "self_attention":
+        emb = torch.randn(2, 8, 32, generator=g)
+        # proba 1.0: every sample uses the learned mask embedding (deterministic), so the
+        # gradient reaches `fixed_embedding` through torch.where
+        proba = 1.0 if case.endswith("all_masked") else 0.0
+        kw_ref = dict(embedding=emb, embedding_mask_proba=proba)
+        kw = dict(embedding=emb.to(DEV), embedding_mask_proba=proba)
+    loss_ref = oracle_loss(ref.net, x, noise, sigma, **kw_ref)
+    loss_ref.backward()
+    for call in range(3):
+        model.zero_grad(set_to_none=True)
+        loss = fused_v_loss(model.net, x.to(DEV), noise.to(DEV), sigma.to(DEV), **kw)
+        loss.backward()
+        rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+        print(f"{case} call {call}: loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+        assert rel < 2e-3
+        ref_named = [(n, p) for n, p in ref.net.named_parameters() if p.grad is not None]
+        got = [q for (n, p), q in zip(ref.net.named_parameters(), model.net.parameters()) if p.grad is not None]
+        worst, cos = compare_grads(ref_named, got)
+        assert worst < GRAD_TOL and cos > 1 - 1e-3
+    if case.endswith("all_masked"):
+        assert model.net.fixed_embedding.weight.grad is not None
+
+
+@pytest.mark.parametrize("cfg_name", ["noatt", "att"])
+def test_custom_loss_through_differentiable_forward(oracle_port, cfg_name):
+    """DiffusionModel(loss_fn=F.l1_loss): VDiffusion calls net(x_noisy, sigma) and a user loss
+    (reference models.py:28,37; tests/testcustomloss.py:28) -- the net forward carries autograd."""
+    import audio_diffusion_pytorch_b200 as adp
+    cfg = CFG if cfg_name == "noatt" else ATT
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**cfg)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, loss_fn=F.l1_loss, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 2, 4096, generator=g)
+    # identical sigma / noise on both sides: drive the oracle by hand with the GPU's draws
+    torch.manual_seed(77)
+    loss = model(x.to(DEV))
+    loss.backward()
+    torch.manual_seed(77)
+    sigma = torch.rand(2, device=DEV).cpu()
+    noise = torch.randn(2, 2, 4096, device=DEV).cpu()
+    a = torch.cos(sigma * math.pi / 2)[:, None, None]
+    b = torch.sin(sigma * math.pi / 2)[:, None, None]
+    loss_ref = F.l1_loss(ref.net(a * x + b * noise, sigma), a * noise - b * x)
+    loss_ref.backward()
+    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    print(f"l1 loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    # d|e|/de = sign(e): elements whose bf16 error flips the sign contribute O(1) changes
+    assert worst < 0.15 and cos > 1 - 5e-3
+
+
+def test_input_gradients_of_the_differentiable_forward(oracle_port):
+    """d v / d x and d v / d append_channels (the DiffusionVocoder trains `to_flat` through it)."""
+    import audio_diffusion_pytorch_b200 as adp
+    kw = {k: v for k, v in CFG.items() if k != "in_channels"}
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **kw)
+    model = adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2, **kw).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 2, 4096, generator=g, requires_grad=True)
+    app = torch.randn(2, 2, 4096, generator=g, requires_grad=True)
+    sigma = torch.rand(2, generator=g)
+    wgt = torch.randn(2, 2, 4096, generator=g)
+    (ref.net(x, sigma, append_channels=app) * wgt).sum().backward()
+    xg = x.detach().to(DEV).requires_grad_(True)
+    ag = app.detach().to(DEV).requires_grad_(True)
+    v = model.net(xg, sigma.to(DEV), append_channels=ag)
+    (v * wgt.to(DEV)).sum().backward()
+    for name, got, want in (("dx", xg.grad, x.grad), ("d append", ag.grad, app.grad)):
+        e = float((got.cpu() - want).norm() / want.norm())
+        print(f"{name}: rel-L2 {e:.3e}")
+        assert e < 2e-2
+
+
+def test_vocoder_forward_trains_to_flat(oracle_port):
+    """DiffusionVocoder.forward (reference models.py:203-209): mel -> to_flat -> append_channels.
+    Loss parity and the gradient of `to_flat.weight` (it only receives one through d append)."""
+    import audio_diffusion_pytorch_b200 as adp
+    kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True,
+              channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionVocoderPort(**kw)
+    model = adp.DiffusionVocoder(net_t=adp.UNetV0, **kw).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.to_flat.load_state_dict(ref.to_flat.state_dict())
+    g = torch.Generator().manual_seed(9)
+    audio = torch.randn(2, 2, 4096, generator=g)
+    torch.manual_seed(31)
+    loss = model(audio.to(DEV))
+    loss.backward()
+    # the same sigma / noise draws for the oracle (drawn on the GPU generator, rows = b*c)
+    torch.manual_seed(31)
+    sigma = torch.rand(4, device=DEV).cpu()
+    noise = torch.randn(4, 1, 4096, device=DEV).cpu()
+    mel = ref.to_spectrogram(audio)
+    guide = ref.to_flat(mel.reshape(-1, *mel.shape[-2:]))
+    rows = audio.reshape(-1, 1, audio.shape[-1])
+    loss_ref = oracle_loss(ref.net, rows, noise, sigma, append_channels=guide)
+    loss_ref.backward()
+    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    print(f"vocoder loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    got, want = model.to_flat.weight.grad, ref.to_flat.weight.grad
+    assert got is not None, "to_flat.weight received no gradient"
+    e = float((got.cpu() - want).norm() / want.norm())
+    print(f"to_flat.weight.grad rel-L2 {e:.3e}")
+    assert e < GRAD_TOL
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < GRAD_TOL and cos > 1 - 1e-3
+
+
+def test_gradient_accumulation_and_zero_grad_in_place(oracle_port):
+    """.grad must not alias the plan's arenas: two backward passes accumulate g1 + g2, and
+    zero_grad(set_to_none=False) followed by a backward gives exactly that backward's gradient."""
+    import audio_diffusion_pytorch_b200 as adp
+    from audio_diffusion_pytorch_b200.training import fused_v_loss
+    _, model = _pair(oracle_port, adp, CFG)
+    g = torch.Generator().manual_seed(12)
+    xs = [torch.randn(2, 2, 4096, generator=g).to(DEV) for _ in range(2)]
+    ns = [torch.randn(2, 2, 4096, generator=g).to(DEV) for _ in range(2)]
+    sg = [torch.rand(2, generator=g).to(DEV) for _ in range(2)]
+    singles = []
+    for i in range(2):
+        model.zero_grad(set_to_none=True)
+        fused_v_loss(model.net, xs[i], ns[i], sg[i]).backward()
+        singles.append([p.grad.clone() for p in model.net.parameters()])
+    model.zero_grad(set_to_none=True)
+    for i in range(2):
+        fused_v_loss(model.net, xs[i], ns[i], sg[i]).backward()
+    for p, g1, g2 in zip(model.net.parameters(), *singles):
+        want = g1 + g2
+        assert float((p.grad - want).norm()) <= 2e-3 * float(want.norm()) + 1e-12
+    model.zero_grad(set_to_none=False)
+    fused_v_loss(model.net, xs[0], ns[0], sg[0]).backward()
+    for p, g1 in zip(model.net.parameters(), singles[0]):
+        assert float((p.grad - g1).norm()) <= 2e-3 * float(g1.norm()) + 1e-12
+
+
+def test_stale_plan_raises(oracle_port):
+    """Two forwards on one shape before a backward: the first graph's activations are gone."""
+    import audio_diffusion_pytorch_b200 as adp
+    from audio_diffusion_pytorch_b200.training import fused_v_loss
+    _, model = _pair(oracle_port, adp, CFG)
+    x = torch.randn(2, 2, 4096, device=DEV)
+    l1 = fused_v_loss(model.net, x, torch.randn_like(x), torch.rand(2, device=DEV))
+    l2 = fused_v_loss(model.net, x, torch.randn_like(x), torch.rand(2, device=DEV))
+    l2.backward()
+    with pytest.raises(RuntimeError, match="another forward"):
+        l1.backward()
+
+
+def test_untracked_weight_update_is_seen_by_inference(oracle_port):
+    """EMA-style `p.data.copy_()` updates bump no version counter: the inference
+    entry points fingerprint the parameters and re-pack."""
+    import audio_diffusion_pytorch_b200 as adp
+    ref, model = _pair(oracle_port, adp, CFG)
+    x = torch.randn(2, 2, 4096, device=DEV)
+    sig = torch.rand(2, device=DEV)
+    v0 = model.net(x, sig).clone()
+    with torch.no_grad():
+        for p in model.net.parameters():
+            p.data.mul_(1.05)
+        for p in ref.net.parameters():
+            p.mul_(1.05)
+        v1 = model.net(x, sig)
+        v_ref = ref.net(x.cpu(), sig.cpu())
+    assert float((v1 - v0).norm()) > 0, "stale packed weights"
+    e = float(((v1.cpu() - x.cpu()) - (v_ref - x.cpu())).norm() / (v_ref - x.cpu()).norm())
+    print(f"after .data update: branch rel-L2 {e:.3e}")
+    assert e < 1.2e-2
+
+
+def test_nine_level_gradients(oracle_port):
+    """The 9-level attention-free shape of BASELINE configs[3] (DiffusionUpsampler channels up to
+    1024: split-K wgrad, C = 1024 dgrad) at a short length the CPU oracle back-propagates in seconds."""
+    import audio_diffusion_pytorch_b200 as adp
+    from audio_diffusion_pytorch_b200.training import fused_v_loss
+    kw = dict(channels=[8, 32, 64, 128, 256, 512, 512, 1024, 1024], factors=[1, 4, 4, 4, 2, 2, 2, 2, 2],
+              items=[1, 2, 2, 2, 2, 2, 2, 4, 4])
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **kw)
+    model = adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2, **kw).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    g = torch.Generator().manual_seed(13)
+    T = 2 ** 14
+    x = torch.randn(2, 2, T, generator=g)
+    noise = torch.randn(2, 2, T, generator=g)
+    sigma = torch.rand(2, generator=g)
+    app = ref.reupsample(x)
+    loss_ref = oracle_loss(ref.net, x, noise, sigma, append_channels=app)
+    loss_ref.backward()
+    loss = fused_v_loss(model.net, x.to(DEV), noise.to(DEV), sigma.to(DEV), append_channels=app.to(DEV))
+    loss.backward()
+    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    print(f"9-level loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < 0.1 and cos > 1 - 2e-3
