@@ -43,7 +43,8 @@ inline cudaError_t ensure_dyn_smem(Kern kernel, size_t bytes, SmemAttrCache& cac
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   size_t& cur = cache.set[dev & 63];
-  if (cur == 0) cur = 48 * 1024;               // the default limit needs no opt-in
+  // always opt in on first use: static + dynamic shared memory together may exceed the 48 KB
+  // default even when the dynamic part alone does not
   if (bytes <= cur) return cudaSuccess;
   e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e == cudaSuccess) cur = bytes;

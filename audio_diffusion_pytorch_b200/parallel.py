@@ -77,3 +77,127 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], bucket_mb: float =
         if nbytes >= bucket_mb * 2 ** 20:
             flush()
     flush()
+
+
+# ----------------------------------------------------------------- overlapped gradient all-reduce
+def merge_intervals(intervals):
+    """Union of half-open [a, b) ranges as a sorted list of maximal ranges."""
+    out: List[List[int]] = []
+    for a, b in sorted((int(a), int(b)) for a, b in intervals if b > a):
+        if out and a <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], b)
+        else:
+            out.append([a, b])
+    return [(a, b) for a, b in out]
+
+
+def bucket_schedule(marks, bucket_elems: int):
+    """marks: gradient-arena ranges in the order the backward program completes them.  Returns
+    {index of the mark after which to communicate: [maximal contiguous ranges]} such that every
+    flush carries >= bucket_elems elements (the last one takes the remainder)."""
+    sched, pending, size = {}, [], 0
+    for i, (a, b) in enumerate(marks):
+        pending.append((a, b))
+        size += b - a
+        if size >= bucket_elems or i == len(marks) - 1:
+            merged = merge_intervals(pending)
+            if merged:
+                sched[i] = merged
+            pending, size = [], 0
+    return sched
+
+
+class _Done:
+    def wait(self):
+        return True
+
+
+def average_async(t: Tensor, group=None):
+    """In-place mean over ranks; returns a handle with .wait().  NCCL: ReduceOp.AVG, asynchronous
+    on NCCL's stream.  Other backends (gloo in the CPU tests): sum, then scale, synchronously."""
+    if dist.get_backend(group) == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=True)
+    dist.all_reduce(t, group=group)
+    t.div_(dist.get_world_size(group))
+    return _Done()
+
+
+class GradSync:
+    """Attached to a B200UNet (`net._grad_sync`) by OverlappedDataParallel: training.py calls it
+    from inside the backward program."""
+
+    def __init__(self, process_group=None, bucket_mb: float = 64.0):
+        self.group = process_group
+        self.bucket_elems = int(bucket_mb * 2 ** 20 / 4)
+        self.world = dist.get_world_size(process_group)
+
+    def flush_schedule(self, plan):
+        if not plan.mark_log:
+            return None
+        if getattr(plan, "_flush", None) is None:
+            plan._flush = bucket_schedule(plan.mark_log, self.bucket_elems)
+        return plan._flush
+
+    def all_reduce_async(self, t: Tensor):
+        return average_async(t, self.group)
+
+    @torch.no_grad()
+    def conditioning_gradients(self, plan) -> None:
+        """dW_cond / db_cond averaged over ranks WITHOUT all-reducing the [47 K x 1024] matrix:
+        gather the rank-B factors (dss [B, n], cond [B, 1024]) and redo the small product."""
+        from . import ops
+        B, Fm = plan.cond.shape
+        n = plan.dss_all.shape[1]
+        dss_g = torch.empty(self.world * B, n, device=plan.dss_all.device)
+        cond_g = torch.empty(self.world * B, Fm, device=plan.dss_all.device)
+        dist.all_gather_into_tensor(dss_g, plan.dss_all.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(cond_g, plan.cond_bf.view(B, Fm).float(), group=self.group)
+        scratch = torch.zeros(self.world * B, Fm, device=plan.dss_all.device)
+        ops.cond_bwd(dss_g, cond_g, plan.P["cond_w"], plan.dw_all, plan.dbias_all, scratch, plan.n_tot)
+        plan.dw_all.div_(self.world)
+        plan.dbias_all.div_(self.world)
+
+
+class OverlappedDataParallel(torch.nn.Module):
+    """Data parallelism for the training step of the B200 path: replicas + ONE
+    gradient average per step over NCCL, overlapped with the hand-written backward program.
+
+        ddp = OverlappedDataParallel(model)            # broadcasts rank 0's weights
+        loss = ddp(x); loss.backward(); ddp.finish_gradient_sync(); opt.step()
+
+    The U-Net's gradients are averaged inside `loss.backward()` (bucketed, each bucket's all-reduce
+    issued as soon as the backward program has finished it); `finish_gradient_sync()` averages the
+    handful of parameters whose gradients come from PyTorch autograd (time-embedding MLP, the
+    vocoder's `to_flat`, the guidance mask embedding).  Every backward synchronises (no `no_sync`
+    gradient accumulation)."""
+
+    def __init__(self, module: torch.nn.Module, process_group=None, bucket_mb: float = 64.0):
+        super().__init__()
+        from .unet import B200UNet
+        self.module = module
+        self.group = process_group
+        nets = [m for m in module.modules() if isinstance(m, B200UNet)]
+        assert len(nets) == 1, "OverlappedDataParallel wraps a model with exactly one B200UNet"
+        self.net = nets[0]
+        self.net._grad_sync = GradSync(process_group, bucket_mb)
+        with torch.no_grad():
+            for p in module.parameters():
+                dist.broadcast(p, src=0, group=process_group)
+        from .training import _net_params
+        inside = {id(p) for p in _net_params(self.net)}
+        self.outside = [p for p in module.parameters() if id(p) not in inside]
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    @torch.no_grad()
+    def finish_gradient_sync(self) -> None:
+        grads = [p.grad for p in self.outside if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        average_async(flat, self.group).wait()
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()

@@ -42,6 +42,14 @@ class _TrainPlan:
         self.graph_f = self.graph_b = None
         self.runs_f = self.runs_b = 0
         self.generation = 0
+        self.on_mark = None          # callable(interval) while a gradient all-reduce is overlapped
+        self.seg_graphs = None       # backward captured as segments cut at the flush marks
+        self.mark_log: List = []     # intervals in execution order (recorded on the eager run)
+
+    def mark(self, interval) -> None:
+        """A contiguous range [start, end) of the gradient arena is final (see level())."""
+        if self.on_mark is not None:
+            self.on_mark(interval)
 
 
 def _zeros(shape, dev, dtype=torch.float32):
@@ -331,6 +339,11 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         lv, Lp = levels[i], P["levels"][i]
         Tl, C = T_in // lv.factor, lv.ch
         innermost = i == len(levels) - 1
+        # gradient-arena cursor at the level's sequence points: the arena is laid out in FORWARD
+        # build order, so "down part", "inner levels" and "up part" of a level are three
+        # contiguous ranges; the backward finishes them in the order up, inner, down and
+        # announces each range through plan.mark (overlapped gradient all-reduce, parallel.py)
+        cur = {"entry": cursor[0]}
         x0, st0 = act(B, Tl, C), new_stats()
         db_down = grad_for(lv.down.bias)
         if i == 0:
@@ -348,10 +361,12 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             finals.append(lambda: grads.__setitem__(
                 id(lv.down.weight), gw_down.view(C, lv.factor, lv.in_ch).permute(0, 2, 1)))
         x, st, items_down_bwd = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl)
+        cur["down_end"] = cursor[0]
         inner = None
         skip = x
         if not innermost:
             x, st, inner = level(i + 1, skip, Tl)
+        cur["inner_end"] = cursor[0]
         x, st, items_up_bwd = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl)
         gate = ss_all[:, Lp["gate_off"]:]
         dgate = dss_all[:, Lp["gate_off"]:]
@@ -381,12 +396,15 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                 for b_ in reversed(items_up_bwd):
                     d = b_(d)
                 if inner is not None:
+                    plan.mark((cur["inner_end"], cur["exit"]))
                     d = inner(d)
                 for b_ in reversed(items_down_bwd):
                     d = b_(d)
                 ops.stem_in_bwd(d, plan.x, dw_down, db_down, lv.factor, append=plan.append,
                                 noise=plan.noise, alpha=plan.alpha, beta=plan.beta,
                                 w=Lp["down_w"], dxin=plan.dxin)
+                plan.mark((cur["entry"], cur["down_end"] if inner is not None else cur["exit"]))
+            cur["exit"] = cursor[0]
             return None, None, backward_level0
 
         # levels >= 1: up conv writes y (pre-gate), skip_gate merges with the level's input
@@ -454,17 +472,20 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             for b_ in reversed(items_up_bwd):
                 d = b_(d)
             if inner is not None:
+                plan.mark((cur["inner_end"], cur["exit"]))
                 d = inner(d)
             for b_ in reversed(items_down_bwd):
                 d = b_(d)
             ops.colsum(d, db_down)
             kdim = lv.factor * lv.in_ch
             ops.wgrad(d, x_in.view(B, Tl, kdim), gw_down, n=C, k=kdim, off=0)
+            plan.mark((cur["entry"], cur["down_end"] if inner is not None else cur["exit"]))
             # gradient w.r.t. the level input = dgrad(down conv) + the skip path (d_out)
             ops.conv_gemm(d, wd_down, d_xin.view(B, Tl, kdim), c_in=C, n_valid=kdim,
                           residual=d_out.view(B, Tl, kdim))
             return d_xin
 
+        cur["exit"] = cursor[0]
         return out, ost, backward_level
 
     _, _, backward0 = level(0, None, T)
@@ -489,6 +510,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         ops.cond_bwd(dss_all, plan.cond_bf.view(B, Fm).float(), P["cond_w"], plan.dw_all,
                      plan.dbias_all, plan.dcond, n_tot)
     plan.backward_program = backward_program
+    plan.P, plan.n_dss = P, dss_all.numel()
     return plan
 
 
@@ -517,9 +539,77 @@ def _run(plan: _TrainPlan, which: str, use_graph: bool) -> None:
         plan.runs_b += 1
 
 
+def _run_backward_synced(plan: _TrainPlan, net: B200UNet, sync) -> None:
+    """Data-parallel backward: the program runs as graph SEGMENTS cut where a bucket of the
+    gradient arena is complete; the bucket's all-reduce (NCCL, async on its own stream) is issued
+    right after the segment's replay and overlaps the remaining segments.  The gradients of the
+    concatenated conditioning projection (48 M of the 175 M parameters of the 9-level net, final
+    only at the very end) are not all-reduced at all: dW = sum_ranks dss_r^T cond_r is recomputed
+    from the all-gathered [world*B, .] factors (a few MB)."""
+    works: List = []
+    flush = sync.flush_schedule(plan)            # {mark index: [intervals to reduce now]}
+    counter = [0]
+
+    def reduce_now(intervals):
+        for a, b in intervals:
+            works.append(sync.all_reduce_async(plan.flat[a:b]))
+
+    record = flush is None                       # no synced backward of this plan has run yet
+    if not net.use_cuda_graph or record:
+        def on_mark(iv):
+            if record:
+                plan.mark_log.append(iv)
+            todo = flush.get(counter[0]) if flush is not None else None
+            counter[0] += 1
+            if todo:
+                reduce_now(todo)
+        plan.on_mark = on_mark
+        plan.backward_program()
+        plan.on_mark = None
+        if record:                               # the mark sequence was just recorded
+            flush = sync.flush_schedule(plan)
+            reduce_now([iv for ivs in flush.values() for iv in ivs])
+    else:
+        if plan.seg_graphs is None:
+            segs: List = []
+            pool = torch.cuda.graph_pool_handle()
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                state = {"g": torch.cuda.CUDAGraph()}
+                state["g"].capture_begin(pool=pool)
+
+                def on_mark(iv):
+                    todo = flush.get(counter[0])
+                    counter[0] += 1
+                    if todo:
+                        state["g"].capture_end()
+                        segs.append((state["g"], todo))
+                        state["g"] = torch.cuda.CUDAGraph()
+                        state["g"].capture_begin(pool=pool)
+                plan.on_mark = on_mark
+                plan.backward_program()
+                plan.on_mark = None
+                state["g"].capture_end()
+                segs.append((state["g"], None))
+            torch.cuda.current_stream().wait_stream(side)
+            plan.seg_graphs = segs
+        for g, todo in plan.seg_graphs:
+            g.replay()
+            if todo:
+                reduce_now(todo)
+    plan.runs_b += 1
+    sync.conditioning_gradients(plan)
+    for w in works:
+        w.wait()
+
+
 class _UNetFn(torch.autograd.Function):
-    """mode 'loss' -> scalar MSE loss; mode 'v' -> v [B, out, T].  Inputs that may receive a
-    gradient: x, append, cond (SiLU of the time features), embedding, and every parameter."""
+    """mode 'loss' -> scalar MSE loss; mode 'v' / 'v1' -> v [B, out, T] ('v1' = a second plan of
+    the same shape, for the masked pass of classifier-free guidance under autograd).  Inputs that
+    may receive a gradient: x, append, cond (SiLU of the time features), embedding, and every
+    parameter."""
 
     @staticmethod
     def forward(ctx, net: B200UNet, mode: str, x, noise, sigmas, append, cond, embedding, *params):
@@ -528,6 +618,7 @@ class _UNetFn(torch.autograd.Function):
         need = ctx.needs_input_grad       # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
         want_dxin = bool(need[2] or need[5])
         key = ("train", B, T, M, mode, want_dxin)
+        slot, mode = mode, ("loss" if mode == "loss" else "v")
         net.packed()                         # in-place refresh of the forward packs
         plan = net._plans.get(key)
         if plan is None:
@@ -572,7 +663,11 @@ class _UNetFn(torch.autograd.Function):
             plan.gscale.copy_(grad_out.reshape(1))
         else:
             plan.dv.copy_(grad_out)
-        _run(plan, "b", net.use_cuda_graph)
+        sync = getattr(net, "_grad_sync", None)
+        if sync is None:
+            _run(plan, "b", net.use_cuda_graph)
+        else:
+            _run_backward_synced(plan, net, sync)
         for fin in plan.finals:
             fin()
         out = []
@@ -618,25 +713,23 @@ def _time_cond(net: B200UNet, sigmas: Optional[Tensor], features: Optional[Tenso
     return F.silu(f)
 
 
-def _train_embedding(net: B200UNet, B: int, embedding: Optional[Tensor], embedding_scale: float,
-                     embedding_mask_proba: float) -> Optional[Tensor]:
+def _train_embedding(net: B200UNet, B: int, embedding: Optional[Tensor],
+                     embedding_mask_proba: float):
     """a_unet ClassifierFreeGuidancePlugin at training time: per-sample Bernoulli swap with the
-    learned mask embedding (PyTorch ops, so its gradient reaches `fixed_embedding`)."""
+    learned mask embedding (PyTorch ops, so its gradient reaches `fixed_embedding`).
+    Returns (embedding fed to the net, the mask embedding or None)."""
+    fixed = None
     if net.use_embedding_cfg:
         assert embedding is not None, "ClassiferFreeGuidancePlugin requires embedding"
-        if embedding_scale != 1.0:
-            raise NotImplementedError(
-                "embedding_scale != 1 under autograd (two guided evaluations with gradients) is "
-                "outside the built path; guidance is a sampling-time feature -- call under no_grad")
+        fixed = net.fixed_embedding.weight[: embedding.shape[1]].unsqueeze(0).expand_as(embedding)
         if embedding_mask_proba > 0.0:
-            fixed = net.fixed_embedding.weight[: embedding.shape[1]].unsqueeze(0).expand_as(embedding)
             mask = torch.bernoulli(torch.full((B, 1, 1), float(embedding_mask_proba),
                                               device=embedding.device)).to(torch.bool)
             embedding = torch.where(mask, fixed, embedding)
     if any(net.cross_attentions):
         assert embedding is not None, "CrossAttentionItem requires embedding"
-        return embedding.float()
-    return None
+        return embedding.float(), (None if fixed is None else fixed.float())
+    return None, None
 
 
 def _net_params(net: B200UNet):
@@ -652,8 +745,18 @@ def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
     """mse(net(alpha*x + beta*noise, sigma), alpha*noise - beta*x)  (reference diffusion.py:90-95)."""
     assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
     assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
+    if net.use_embedding_cfg and embedding_scale != 1.0:
+        # guidance inside the training objective = two differentiable evaluations (a_unet CFG
+        # plugin); no fused-loss form: take the generic route
+        sig_b = sigmas.view(-1, 1, 1)
+        alphas, betas = torch.cos(sig_b * pi / 2), torch.sin(sig_b * pi / 2)
+        v = differentiable_forward(net, alphas * x + betas * noise, sigmas, features=features,
+                                   embedding=embedding, embedding_scale=embedding_scale,
+                                   embedding_mask_proba=embedding_mask_proba,
+                                   append_channels=append_channels)
+        return F.mse_loss(v, alphas * noise - betas * x)
     cond = _time_cond(net, sigmas, features)
-    emb = _train_embedding(net, x.shape[0], embedding, embedding_scale, embedding_mask_proba)
+    emb, _ = _train_embedding(net, x.shape[0], embedding, embedding_mask_proba)
     return _UNetFn.apply(net, "loss", x.float(), noise.float(), sigmas, append_channels, cond, emb,
                          *_net_params(net))
 
@@ -665,6 +768,12 @@ def differentiable_forward(net: B200UNet, x: Tensor, time: Optional[Tensor], *,
     """v = net(x, time, ...) with autograd support (custom loss_fn / diffusion_t)."""
     assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
     cond = _time_cond(net, time, features)
-    emb = _train_embedding(net, x.shape[0], embedding, embedding_scale, embedding_mask_proba)
-    v = _UNetFn.apply(net, "v", x.float(), None, time, append_channels, cond, emb, *_net_params(net))
+    emb, fixed = _train_embedding(net, x.shape[0], embedding, embedding_mask_proba)
+    params = _net_params(net)
+    v = _UNetFn.apply(net, "v", x.float(), None, time, append_channels, cond, emb, *params)
+    if net.use_embedding_cfg and embedding_scale != 1.0:
+        # a_unet ClassifierFreeGuidancePlugin: out_masked + (out - out_masked) * scale, both passes
+        # differentiable (a second plan of the same shape keeps the first one's activations alive)
+        v_m = _UNetFn.apply(net, "v1", x.float(), None, time, append_channels, cond, fixed, *params)
+        v = v_m + (v - v_m) * embedding_scale
     return v.to(x.dtype)

@@ -42,6 +42,18 @@ def _worker(rank, world, port, out_dir):
     num = sum(float((p.grad - f).double().norm() ** 2) for p, f in zip(model.parameters(), full))
     den = sum(float(f.double().norm() ** 2) for f in full)
     rel = (num / den) ** 0.5
+    # overlapped all-reduce inside the backward program (eager run, capture, replay)
+    odp = parallel.OverlappedDataParallel(model, bucket_mb=0.05)
+    rel_o = 0.0
+    for _ in range(3):
+        model.zero_grad()
+        fused_v_loss(model.net, x[lo:hi], noise[lo:hi], sigma[lo:hi]).backward()
+        odp.finish_gradient_sync()
+        num = sum(float((p.grad - f).double().norm() ** 2) for p, f in zip(model.parameters(), full)
+                  if p.grad is not None)
+        rel_o = max(rel_o, (num / den) ** 0.5)
+    n_seg = len(model.net._plans[("train", hi - lo, 4096, 0, "loss", False)].seg_graphs)
+    model.net._grad_sync = None
     # DDP wrapper around the reference training call
     ddp = DDP(model, device_ids=[rank])
     model.zero_grad()
@@ -57,14 +69,16 @@ def _worker(rank, world, port, out_dir):
     s_shard = parallel.sample_sharded(model, noise, 3)
     rel_s = float((s_shard - s_full).norm() / s_full.norm())
     if rank == 0:
-        open(os.path.join(out_dir, "result"), "w").write(f"{rel} {grads_ok} {same} {rel_s}")
+        open(os.path.join(out_dir, "result"), "w").write(f"{rel} {grads_ok} {same} {rel_s} {rel_o} {n_seg}")
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_gradients_and_sampling(tmp_path):
     mp.spawn(_worker, args=(2, 29600 + os.getpid() % 2000, str(tmp_path)), nprocs=2, join=True)
-    rel, grads_ok, same, rel_s = open(tmp_path / "result").read().split()
+    rel, grads_ok, same, rel_s, rel_o, n_seg = open(tmp_path / "result").read().split()
     print("DP gradient rel-L2 vs full batch:", rel, "DDP grads finite:", grads_ok,
-          "identical across ranks:", same, "sharded sampling rel-L2:", rel_s)
+          "identical across ranks:", same, "sharded sampling rel-L2:", rel_s,
+          "overlapped all-reduce rel-L2:", rel_o, "backward graph segments:", n_seg)
     assert float(rel) < 2e-2 and grads_ok == "True" and same == "True" and float(rel_s) < 2e-3
+    assert float(rel_o) < 2e-2 and int(n_seg) >= 2

@@ -40,6 +40,13 @@ def fingerprint(module):
                      float(sum(p.numel() for p in ps))])
 
 
+@pytest.fixture(autouse=True)
+def inference_mode():
+    """This file tests the inference path (training parity: test_train_gpu.py)."""
+    with torch.no_grad():
+        yield
+
+
 @pytest.fixture(scope="module")
 def adp():
     import audio_diffusion_pytorch_b200 as adp
@@ -118,9 +125,10 @@ def test_text_cfg_vs_golden(adp, oracle_port, golden_dir):
     model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY_TEXT).to(DEV)
     model.net.load_reference_parameters(ref.net)
     x, sigma, emb = t(g["x"]), t(g["sigma"]), t(g["embedding"])
-    v1 = model.net(x, sigma, embedding=emb)
+    with torch.no_grad():      # inference path (one 2B-row evaluation, guidance fused in the last kernel)
+        v1 = model.net(x, sigma, embedding=emb)
+        v5 = model.net(x, sigma, embedding=emb, embedding_scale=5.0)
     check(v1, torch.from_numpy(g["v_scale1"]), x, "text-cond forward, scale 1")
-    v5 = model.net(x, sigma, embedding=emb, embedding_scale=5.0)
     # guidance extrapolates: v_m + 5 (v_c - v_m) amplifies the error of both passes (|1-s|+|s| = 9x)
     check(v5, torch.from_numpy(g["v_scale5"]), x, "text-cond forward, CFG 5", branch_tol=3e-2,
           v_tol=3e-4)
@@ -265,9 +273,10 @@ def test_cfg3_readme_scale_vs_golden(adp, oracle_port, golden_dir):
     x = torch.randn(1, 2, int(g["length"]), generator=gen)
     emb = torch.randn(1, 64, 768, generator=gen)
     sig = t(g["sigma"])
-    v1 = model.net(x.to(DEV), sig, embedding=emb.to(DEV))
+    with torch.no_grad():
+        v1 = model.net(x.to(DEV), sig, embedding=emb.to(DEV))
+        v5 = model.net(x.to(DEV), sig, embedding=emb.to(DEV), embedding_scale=5.0)
     check(v1, torch.from_numpy(g["v_scale1"]), x, "cfg3 README scale, guidance 1")
-    v5 = model.net(x.to(DEV), sig, embedding=emb.to(DEV), embedding_scale=5.0)
     # guidance extrapolates: v_m + 5 (v_c - v_m) amplifies both passes' error (|1-s| + |s| = 9x on
     # the conditional-unconditional difference); bound 2.5x the single-pass branch tolerance
     check(v5, torch.from_numpy(g["v_scale5"]), x, "cfg3 README scale, CFG 5", branch_tol=3e-2, v_tol=3e-4)

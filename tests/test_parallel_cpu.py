@@ -36,6 +36,31 @@ def _worker(rank, world, port, out_dir):
     noise = torch.arange(10, dtype=torch.float32).reshape(5, 2)
     out = parallel.sample_sharded(Toy(), noise, 3, scale=torch.arange(5, dtype=torch.float32))
     assert torch.equal(out, noise * 3 + torch.arange(5, dtype=torch.float32).view(-1, 1))
+    # OverlappedDataParallel host logic: the parameters whose gradients come from PyTorch autograd
+    # are averaged by finish_gradient_sync; the conditioning-projection gradient is rebuilt from
+    # the gathered rank-B factors instead of all-reducing the full matrix
+    lin = torch.nn.Linear(3, 2)
+    wrapper = parallel.OverlappedDataParallel.__new__(parallel.OverlappedDataParallel)
+    torch.nn.Module.__init__(wrapper)
+    wrapper.group, wrapper.outside = None, list(lin.parameters())
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(10 * (rank + 1)))
+    wrapper.finish_gradient_sync()
+    for p in lin.parameters():
+        assert torch.allclose(p.grad, torch.full_like(p, 10 * (1 + world) / 2))
+    g = torch.Generator().manual_seed(rank)
+    dss, cond = torch.randn(3, 16, generator=g), torch.randn(3, 8, generator=g)
+    local = dss.t() @ cond                                   # this rank's dW
+    want = local.clone()
+    dist.all_reduce(want)
+    gathered_d = [torch.empty_like(dss) for _ in range(world)]
+    gathered_c = [torch.empty_like(cond) for _ in range(world)]
+    dist.all_gather(gathered_d, dss)
+    dist.all_gather(gathered_c, cond)
+    assert torch.allclose(torch.cat(gathered_d).t() @ torch.cat(gathered_c), want, atol=1e-5)
+    t = torch.full((6,), float(rank + 1))
+    parallel.average_async(t).wait()
+    assert torch.allclose(t, torch.full((6,), (1 + world) / 2))
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
@@ -64,3 +89,20 @@ def test_bench_reference_arm_rank_handling():
                         "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bucket_schedule_covers_the_arena_once():
+    """Gradient-arena ranges arrive in backward order (up parts from the end of the arena towards
+    the middle, then down parts towards the start): every element is communicated exactly once,
+    in maximal contiguous ranges, in buckets of at least the requested size."""
+    sys.path.insert(0, ROOT)
+    from audio_diffusion_pytorch_b200.parallel import bucket_schedule, merge_intervals
+    # arena layout [dss | L0 down | L1 down | L2 (innermost) | L1 up | L0 up]
+    marks = [(900, 1000), (700, 900), (400, 700), (250, 400), (100, 250)]
+    sched = bucket_schedule(marks, bucket_elems=280)
+    sent = [iv for i in sorted(sched) for iv in sched[i]]
+    assert merge_intervals(sent) == [(100, 1000)]
+    assert sum(b - a for a, b in sent) == 900                      # no overlap
+    assert all(sum(b - a for a, b in sched[i]) >= 280 for i in sorted(sched)[:-1])
+    assert max(sched) == len(marks) - 1                            # the last mark always flushes
+    assert merge_intervals([(5, 7), (1, 3), (3, 5), (9, 9)]) == [(1, 7)]

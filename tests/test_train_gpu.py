@@ -30,7 +30,8 @@ def compare_grads(ref_params, got_params):
     worst, dots, n1, n2 = 0.0, 0.0, 0.0, 0.0
     # gradients that are analytically zero (a conv bias feeding a GroupNorm with one channel per
     # group) are compared on the scale of a typical parameter gradient, not on their own
-    floor = 0.1 * float(torch.stack([p.grad.double().norm() for _, p in ref_params]).median())
+    norms = torch.stack([p.grad.double().norm() for _, p in ref_params])
+    floor = max(0.1 * float(norms.median()), 1e-3 * float(norms.max()))
     for (name, p), q in zip(ref_params, got_params):
         assert q.grad is not None, f"no gradient for {name}"
         g_ref, g = p.grad.double(), q.grad.double().cpu()
@@ -273,13 +274,16 @@ def test_gradient_accumulation_and_zero_grad_in_place(oracle_port):
     model.zero_grad(set_to_none=True)
     for i in range(2):
         fused_v_loss(model.net, xs[i], ns[i], sg[i]).backward()
+    # run-to-run reproducibility is ~1e-4 (GroupNorm statistics accumulate with atomics); gradients
+    # that are analytically zero are compared on the scale of a typical gradient
+    floor = 0.1 * float(torch.stack([g_.norm() for g_ in singles[0]]).median())
     for p, g1, g2 in zip(model.net.parameters(), *singles):
         want = g1 + g2
-        assert float((p.grad - want).norm()) <= 2e-3 * float(want.norm()) + 1e-12
+        assert float((p.grad - want).norm()) <= 2e-3 * max(float(want.norm()), floor)
     model.zero_grad(set_to_none=False)
     fused_v_loss(model.net, xs[0], ns[0], sg[0]).backward()
     for p, g1 in zip(model.net.parameters(), singles[0]):
-        assert float((p.grad - g1).norm()) <= 2e-3 * float(g1.norm()) + 1e-12
+        assert float((p.grad - g1).norm()) <= 2e-3 * max(float(g1.norm()), floor)
 
 
 def test_stale_plan_raises(oracle_port):
@@ -300,14 +304,16 @@ def test_untracked_weight_update_is_seen_by_inference(oracle_port):
     entry points fingerprint the parameters and re-pack."""
     import audio_diffusion_pytorch_b200 as adp
     ref, model = _pair(oracle_port, adp, CFG)
+    torch.manual_seed(1)
+    other = oracle_port.DiffusionModelPort(**CFG)          # a second set of weights
     x = torch.randn(2, 2, 4096, device=DEV)
     sig = torch.rand(2, device=DEV)
-    v0 = model.net(x, sig).clone()
     with torch.no_grad():
-        for p in model.net.parameters():
-            p.data.mul_(1.05)
-        for p in ref.net.parameters():
-            p.mul_(1.05)
+        v0 = model.net(x, sig).clone()
+        for p, q in zip(model.net.parameters(), other.net.parameters()):
+            p.data.lerp_(q.to(DEV), 0.5)                   # EMA-style update through .data
+        for p, q in zip(ref.net.parameters(), other.net.parameters()):
+            p.lerp_(q, 0.5)
         v1 = model.net(x, sig)
         v_ref = ref.net(x.cpu(), sig.cpu())
     assert float((v1 - v0).norm()) > 0, "stale packed weights"
@@ -341,4 +347,23 @@ def test_nine_level_gradients(oracle_port):
     print(f"9-level loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < 0.1 and cos > 1 - 2e-3
+
+
+def test_guidance_under_autograd(oracle_port):
+    """embedding_scale != 1 with gradients enabled: two differentiable evaluations combined as
+    out_masked + (out - out_masked) * scale (a_unet ClassifierFreeGuidancePlugin)."""
+    import audio_diffusion_pytorch_b200 as adp
+    ref, model = _pair(oracle_port, adp, TEXT)
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(2, 2, 4096, generator=g)
+    sigma = torch.rand(2, generator=g)
+    emb = torch.randn(2, 8, 32, generator=g)
+    wgt = torch.randn(2, 2, 4096, generator=g)
+    (ref.net(x, sigma, embedding=emb, embedding_scale=3.0) * wgt).sum().backward()
+    v = model.net(x.to(DEV), sigma.to(DEV), embedding=emb.to(DEV), embedding_scale=3.0)
+    (v * wgt.to(DEV)).sum().backward()
+    ref_named = [(n, p) for n, p in ref.net.named_parameters() if p.grad is not None]
+    got = [q for (n, p), q in zip(ref.net.named_parameters(), model.net.parameters()) if p.grad is not None]
+    worst, cos = compare_grads(ref_named, got)
     assert worst < 0.1 and cos > 1 - 2e-3
