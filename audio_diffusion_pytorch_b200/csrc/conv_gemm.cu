@@ -24,7 +24,7 @@
 
 namespace adp {
 
-// diagnostic switches (adp_debug_set): [0] unused; [2] 1 = weights are not
+// diagnostic switches (adp_debug_set): [0] 3 = CTA-pair (cta_group::2) GEMMs; [2] 1 = weights are not
 // written by the preceding kernels (fetch them before griddepcontrol.wait); [3] CTAs/SM override;
 // [4] bit0 skip MMAs, bit1 skip TMA loads, bit2 skip drain, bit3 exit at entry (timing
 // experiments only); [5] KC override; [6] PDL; [7] 1 = never use the 8-epilogue-warp variant
@@ -40,7 +40,7 @@ struct Gemm2Params {
   const float* bias;
   const float* gate;
   double* stats;
-  int T, tiles_per_batch, c_in, ldo;
+  int B, T, tiles_per_batch, c_in, ldo;
   int n_pad, n_valid;
   int ntaps, tap_off0, up_factor;
   int groups, group_size, group_shift;   // group_shift >= 0: group = ch >> shift
@@ -63,13 +63,19 @@ struct Gemm2Params {
 
 struct TileInfo {
   int b, t0, n0, phase, ch0, ntaps, min_off;
+  bool valid;       // CTA pairs: the odd CTA of the last pair may have no rows
 };
 
-__device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, int BN) {
+// cg = CTAs per tile (1, or 2 for cta_group::2 pairs: `tile` then indexes PAIR tiles of
+// 2*kBM rows and `rank` selects this CTA's 128 of them)
+__device__ __forceinline__ TileInfo tile_info(const Gemm2Params& p, int tile, int BN, int cg = 1,
+                                              int rank = 0) {
   TileInfo ti;
-  const int m_tile = tile / p.n_tiles_n;
-  const int n_tile = tile - m_tile * p.n_tiles_n;
+  const int m_pair = tile / p.n_tiles_n;
+  const int n_tile = tile - m_pair * p.n_tiles_n;
+  const int m_tile = m_pair * cg + rank;
   ti.b = m_tile / p.tiles_per_batch;
+  ti.valid = ti.b < p.B;
   ti.t0 = (m_tile - ti.b * p.tiles_per_batch) * kBM;
   ti.n0 = n_tile * BN;
   ti.phase = ti.n0 / p.n_pad;
@@ -130,7 +136,13 @@ static __device__ __noinline__ void stats_generic(float* slots, int net, int et,
 // EW = epilogue warps: 4 (one per TMEM lane quarter) or, for the long-K shapes that run one CTA
 // per SM with <= one tile per CTA (nothing to overlap the drain with), 8: two warps per lane
 // quarter, each draining half of the tile's columns.
-template <int BN, int SW, bool XF, int EW>
+// CG = 2: CTA PAIRS (cluster of 2 on one TPC, tcgen05 cta_group::2).  One MMA covers 256 rows x BN:
+// each CTA stages its own 128 rows of A but only HALF of the W tile, so the shared-memory fill
+// traffic per output drops from (A + W) to (A + W/2) per CTA -- the deep-level GEMMs are bound by
+// exactly that L2 -> SMEM traffic (profiles/r2_gemm_traffic.txt).  The leader (cluster rank 0)
+// issues every MMA and multicasts the completion to both CTAs' barriers; both CTAs run their own
+// TMA producer (signalling the LEADER's full barrier) and their own epilogue.
+template <int BN, int SW, bool XF, int EW, int CG = 1>
 __global__ void __launch_bounds__(64 + 32 * EW + (XF ? 256 : 0),
                                   EW == 8 ? 1 : (BN <= 64 ? (XF ? 2 : 3) : (BN <= 128 ? (XF ? 1 : 2) : 1)))
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -138,7 +150,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int BK = SW / 2;
   constexpr int ACC_COLS = BN < 32 ? 32 : BN;     // TMEM columns per accumulator buffer
   constexpr int CH = BN < 32 ? 16 : 32;           // epilogue column chunk
-  constexpr uint32_t kWTapBytes = BN * SW;        // bytes one W box writes
+  constexpr int WN = BN / CG;                     // W rows staged by THIS CTA
+  constexpr uint32_t kWTapBytes = WN * SW;        // bytes one W box writes
+  static_assert(CG == 1 || (CG == 2 && !XF), "CTA pairs: plain (non-transform) variant only");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], ready_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
@@ -161,25 +175,29 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* ring = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
 
-  const int tile_begin = blockIdx.x * p.tiles_per_cta;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const int tile_begin = (blockIdx.x / CG) * p.tiles_per_cta;
   int tile_end = tile_begin + p.tiles_per_cta;
   if (tile_end > p.total_tiles) tile_end = p.total_tiles;
 
   for (int i = threadIdx.x; i < 2 * kMaxGroups * NET; i += blockDim.x) s_part[i] = 0.f;
   if (warp == 0) {
-    tmem_alloc(&tmem_slot, 2 * ACC_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_cg2(&tmem_slot, 2 * ACC_COLS); tmem_relinquish_cg2(); }
+    else { tmem_alloc(&tmem_slot, 2 * ACC_COLS); tmem_relinquish(); }
   } else if (warp == 1 && lane == 0) {
+    // pairs: the leader's full barrier gets its own arrive.expect_tx plus the peer's remote arrive;
+    // the leader's acc_empty collects the epilogue warps of BOTH CTAs
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256);
+      mbar_init(&full_bar[s], CG); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 256);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EW * CG); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // the peer's barriers exist before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_slot, 0);   // warp-uniform for ptxas
   // Programmatic dependent launch: this kernel may have started while its predecessor still
@@ -199,15 +217,22 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (elect_one()) {
           int tile = tile_begin, ks = 0;
           for (int it = 0; it < early; ++it) {          // stage `it` of the (still empty) ring
-            const TileInfo ti = tile_info(p, tile, BN);
+            const TileInfo ti = tile_info(p, tile, BN, CG, rank);
             uint8_t* st = ring + it * p.stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[it],
-                                  static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes));
+            const uint32_t tx_it = static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes);
+            const uint32_t lead_bar = CG == 2 ? mapa_shared(smem_u32(&full_bar[it]), 0) : 0u;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[it], CG * tx_it);
+            else mbar_arrive_cluster(lead_bar);
             for (int c = 0; c < p.kc; ++c) {
               const int k0 = (ks * p.kc + c) * BK;
               uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
-              for (int tap = 0; tap < ti.ntaps; ++tap)
-                tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[it], tap * p.c_in + k0, ti.n0);
+              for (int tap = 0; tap < ti.ntaps; ++tap) {
+                if constexpr (CG == 2)
+                  tma_load_2d_cg2(wdst + tap * p.w_sub_bytes, &tmW, lead_bar, tap * p.c_in + k0,
+                                  ti.n0 + static_cast<int>(rank) * WN);
+                else
+                  tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[it], tap * p.c_in + k0, ti.n0);
+              }
             }
             if (++ks == p.k_stages) { ks = 0; ++tile; }
           }
@@ -218,24 +243,37 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0, it = 0;
       uint32_t ph = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const TileInfo ti = tile_info(p, tile, BN);
+        const TileInfo ti = tile_info(p, tile, BN, CG, rank);
         const uint32_t tx = static_cast<uint32_t>(p.kc) * (a_bytes + ti.ntaps * kWTapBytes);
         for (int ks = 0; ks < p.k_stages; ++ks, ++it) {
           const bool armed = it < early;                 // barrier armed + weights already issued
           if (!armed) mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = ring + s * p.stage_bytes;
           if (elect_one()) {
+            const uint32_t lead_bar = CG == 2 ? mapa_shared(smem_u32(&full_bar[s]), 0) : 0u;
             if (p.dbg & 2) {
-              mbar_arrive(&full_bar[s]);
+              if (rank == 0) mbar_arrive(&full_bar[s]);
+              else mbar_arrive_cluster(lead_bar);
             } else {
-              if (!armed) mbar_arrive_expect_tx(&full_bar[s], tx);
+              if (!armed) {
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], CG * tx);
+                else mbar_arrive_cluster(lead_bar);
+              }
               for (int c = 0; c < p.kc; ++c) {
                 const int k0 = (ks * p.kc + c) * BK;
-                tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
+                if constexpr (CG == 2)
+                  tma_load_3d_cg2(st + c * p.a_sub_bytes, &tmA, lead_bar, k0, ti.t0 + ti.min_off, ti.b);
+                else
+                  tma_load_3d(st + c * p.a_sub_bytes, &tmA, &full_bar[s], k0, ti.t0 + ti.min_off, ti.b);
                 if (armed) continue;
                 uint8_t* wdst = st + p.kc * p.a_sub_bytes + c * p.max_taps * p.w_sub_bytes;
-                for (int tap = 0; tap < ti.ntaps; ++tap)
-                  tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
+                for (int tap = 0; tap < ti.ntaps; ++tap) {
+                  if constexpr (CG == 2)
+                    tma_load_2d_cg2(wdst + tap * p.w_sub_bytes, &tmW, lead_bar, tap * p.c_in + k0,
+                                    ti.n0 + static_cast<int>(rank) * WN);
+                  else
+                    tma_load_2d(wdst + tap * p.w_sub_bytes, &tmW, &full_bar[s], tap * p.c_in + k0, ti.n0);
+                }
               }
             }
           }
@@ -246,8 +284,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------ MMA issuer
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    if (rank == 0) {       // pairs: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN, 0, 0);
       // descriptor of the ring base; byte offsets are added to the 14-bit address field
       const uint64_t desc0 = umma_desc_kmajor<SW>(smem_u32(ring));
       const uint32_t stage_u = static_cast<uint32_t>(p.stage_bytes) >> 4;
@@ -257,7 +295,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 0, j = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
-        const TileInfo ti = tile_info(p, tile, BN);
+        const TileInfo ti = tile_info(p, tile, BN, CG, 0);
         const uint32_t buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -275,15 +313,24 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int tap = 0; tap < ti.ntaps; ++tap) {
 #pragma unroll
                   for (int kk = 0; kk < BK / 16; ++kk) {
-                    umma_bf16(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
-                              wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
+                    if constexpr (CG == 2)
+                      umma_bf16_cg2(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
+                                    wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
+                    else
+                      umma_bf16(d_tmem, adesc + ((tap * SW + kk * 32) >> 4),
+                                wdesc + tap * w_sub_u + ((kk * 32) >> 4), idesc, accumulate);
                     accumulate = 1;
                   }
                 }
               }
             }
-            umma_commit(&empty_bar[s]);
-            if (ks == p.k_stages - 1) umma_commit(&acc_full[buf]);
+            if constexpr (CG == 2) {
+              umma_commit_cg2(&empty_bar[s], 3);
+              if (ks == p.k_stages - 1) umma_commit_cg2(&acc_full[buf], 3);
+            } else {
+              umma_commit(&empty_bar[s]);
+              if (ks == p.k_stages - 1) umma_commit(&acc_full[buf]);
+            }
           }
           accumulate = 1;
           __syncwarp();
@@ -324,13 +371,13 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
 
     for (int tile = tile_begin; tile < tile_end; ++tile, ++j) {
-      const TileInfo ti = tile_info(p, tile, BN);
+      const TileInfo ti = tile_info(p, tile, BN, CG, rank);
       const uint32_t buf = j & 1;
       const int t = ti.t0 + row;
-      const bool row_ok = t < p.T;
-      const size_t row_off = (static_cast<size_t>(ti.b) * p.T + (row_ok ? t : 0)) * p.ldo +
+      const bool row_ok = t < p.T && ti.valid;
+      const size_t row_off = (static_cast<size_t>(ti.valid ? ti.b : 0) * p.T + (row_ok ? t : 0)) * p.ldo +
                              static_cast<size_t>(ti.phase) * p.n_valid;
-      if (do_stats && ti.b != cur_b) {
+      if (do_stats && ti.valid && ti.b != cur_b) {
         if (cur_b >= 0) publish_stats(cur_b);
         cur_b = ti.b;
       }
@@ -349,7 +396,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int ch = ti.ch0 + c;
         const bool ok = ch < p.n_valid;
         s_bias[buf][c] = (p.bias && ok) ? __ldg(p.bias + ch) : 0.f;
-        s_gate[buf][c] = (p.gate && ok) ? __ldg(p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch) : 1.f;
+        s_gate[buf][c] = (p.gate && ok && ti.valid) ? __ldg(p.gate + static_cast<size_t>(ti.b) * p.ld_gate + ch) : 1.f;
       }
       named_bar_sync(2, NET);     // staging visible to all epilogue warps
       mbar_wait(&acc_full[buf], (j >> 1) & 1);
@@ -501,7 +548,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // accumulator buffer drained -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+        else mbar_arrive(&acc_empty[buf]);
+      }
     }
     if (do_stats && cur_b >= 0) publish_stats(cur_b);
   } else if constexpr (XF) {
@@ -571,10 +621,12 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // neither CTA's smem / TMEM / barriers may vanish early
+  else __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, 2 * ACC_COLS);
+    else tmem_dealloc(tmem_base, 2 * ACC_COLS);
   }
 }
 
@@ -589,17 +641,40 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, int SW, bool XF, int EW>
+template <int BN, int SW, bool XF, int EW, int CG = 1>
 static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int occ_in);
+
+// CTA pairs (cta_group::2) are OPT-IN: adp_debug_set(0, 3).  Measured on B200
+// (profiles/r2_gemm_pairs.txt): the pair MMA removes the shared-memory operand-read bound of the
+// 128 x 128 SS-MMA (MMA phase of the L7 conv3 5.5 us instead of 8.1 us), but every ring stage then
+// costs a cross-CTA handshake (multicast commit -> peer producer -> TMA -> leader's barrier,
+// ~1.8 us per round trip) that a 196 KB ring cannot hide: 16.6 us vs 16.2 us end to end.
+template <int BN, int SW, bool XF>
+static bool use_pairs(const adp_conv_gemm_args& a) {
+  if (BN != 128 || SW != 128 || XF || g_debug[0] != 3) return false;
+  const int taps = a.up_factor > 1 ? 2 : a.ntaps;
+  const long m_tiles = (long)a.B * ((a.T + kBM - 1) / kBM);
+  return m_tiles >= 2 && (a.c_in / 64) * taps >= 8;
+}
 
 template <int BN, int SW, bool XF>
 static int launch_gemm2(const adp_conv_gemm_args& a, cudaStream_t stream) {
+  if constexpr (BN == 128 && SW == 128 && !XF) {
+    if (use_pairs<BN, SW, XF>(a)) {
+      const long m_pairs = ((long)a.B * ((a.T + kBM - 1) / kBM) + 1) / 2;
+      const long total = m_pairs * (a.phases * a.n_pad / BN);
+      // <= one pair tile per CTA pair: nothing overlaps the drain -> 8 drain warps
+      if (g_debug[7] == 0 && 2 * total <= 2L * num_sms()) return launch_gemm2_ew<BN, SW, XF, 8, 2>(a, stream, 1);
+      return launch_gemm2_ew<BN, SW, XF, 4, 2>(a, stream, 1);
+    }
+  }
   return launch_gemm2_ew<BN, SW, XF, 4>(a, stream, 0);
 }
 
-template <int BN, int SW, bool XF, int EW>
+template <int BN, int SW, bool XF, int EW, int CG>
 static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int occ_in) {
   constexpr int BK = SW / 2;
+  constexpr int WN = BN / CG;
   const int tiles_per_batch = (a.T + kBM - 1) / kBM;
   const bool up = a.up_factor > 1;
   const int max_taps = up ? 2 : a.ntaps;
@@ -609,7 +684,7 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
 
   Gemm2Params p;
   p.a_sub_bytes = (a_rows * SW + 1023) / 1024 * 1024;
-  p.w_sub_bytes = (BN * SW + 1023) / 1024 * 1024;
+  p.w_sub_bytes = (WN * SW + 1023) / 1024 * 1024;
   p.max_taps = max_taps;
   const int chunk_bytes = p.a_sub_bytes + max_taps * p.w_sub_bytes;
 
@@ -628,7 +703,7 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
     return (o == 1 ? (EW == 8 ? 204 : 196) : (o == 2 ? (XF ? 92 : 96) : 60)) * 1024;   // 227 KB - static - 1 KB
   };  // <= 11 KB static smem/CTA
   while (occ > 1 && budget_of(occ) < 2 * chunk_bytes) --occ;   // need >= 2 stages in the ring
-  if constexpr (EW == 4 && !XF && BN >= 64) {
+  if constexpr (EW == 4 && !XF && BN >= 64 && CG == 1) {
     // at most ~two tiles per SM: little or nothing overlaps the drain -> one CTA per SM with
     // 8 drain warps (also when 2 CTAs/SM were possible but every SM gets <= one tile anyway)
     const long total = (long)a.B * tiles_per_batch * (a.phases * a.n_pad / BN);
@@ -662,18 +737,19 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
   {
     const uint64_t dims[2] = {(uint64_t)a.k_total, (uint64_t)a.phases * a.n_pad};
     const uint64_t strides[1] = {(uint64_t)a.k_total * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)WN};
     if (int e = make_tmap_bf16(&tmW, a.w, 2, dims, strides, box, SW)) return e;
   }
 
   static SmemAttrCache smem_cache;
-  ADP_CUDA(ensure_dyn_smem(conv_gemm2_kernel<BN, SW, XF, EW>, smem, smem_cache));
+  ADP_CUDA(ensure_dyn_smem(conv_gemm2_kernel<BN, SW, XF, EW, CG>, smem, smem_cache));
 
   p.out = static_cast<__nv_bfloat16*>(a.out);
   p.residual = static_cast<const __nv_bfloat16*>(a.residual);
   p.bias = a.bias;
   p.gate = a.gate;
   p.stats = a.stats;
+  p.B = a.B;
   p.T = a.T;
   p.tiles_per_batch = tiles_per_batch;
   p.c_in = a.c_in;
@@ -691,7 +767,7 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
   p.out_fp32 = a.out_fp32;
   p.ld_gate = a.ld_gate > 0 ? a.ld_gate : a.n_valid;
   p.n_tiles_n = a.phases * a.n_pad / BN;
-  p.total_tiles = a.B * tiles_per_batch * p.n_tiles_n;
+  p.total_tiles = (a.B * tiles_per_batch + CG - 1) / CG * p.n_tiles_n;   // pair tiles when CG == 2
   p.a_rows = a_rows;
   p.dbg = g_debug[4];
   p.early_w = g_debug[2];
@@ -701,11 +777,13 @@ static int launch_gemm2_ew(const adp_conv_gemm_args& a, cudaStream_t stream, int
   p.gn_eps = a.gn_eps;
   p.gn_groups = a.gn_groups > 0 ? a.gn_groups : 1;
 
-  int grid = p.total_tiles < occ * num_sms() ? p.total_tiles : occ * num_sms();
+  // grid in units of CTA groups (single CTAs, or pairs)
+  const int slots = occ * num_sms() / CG;
+  int grid = p.total_tiles < slots ? p.total_tiles : slots;
   p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
   grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  ADP_CUDA(launch_k(conv_gemm2_kernel<BN, SW, XF, EW>, dim3(grid), dim3(64 + 32 * EW + (XF ? 256 : 0)), smem, stream, tmA,
-                    tmW, p));
+  ADP_CUDA(launch_k_cluster(conv_gemm2_kernel<BN, SW, XF, EW, CG>, dim3(grid * CG),
+                            dim3(64 + 32 * EW + (XF ? 256 : 0)), smem, stream, CG, tmA, tmW, p));
   ADP_LAUNCH_CHECK();
   return 0;
 }

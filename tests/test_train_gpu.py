@@ -279,11 +279,11 @@ def test_gradient_accumulation_and_zero_grad_in_place(oracle_port):
     floor = 0.1 * float(torch.stack([g_.norm() for g_ in singles[0]]).median())
     for p, g1, g2 in zip(model.net.parameters(), *singles):
         want = g1 + g2
-        assert float((p.grad - want).norm()) <= 2e-3 * max(float(want.norm()), floor)
+        assert float((p.grad - want).norm()) <= 2e-3 * float(want.norm()) + 2e-2 * floor
     model.zero_grad(set_to_none=False)
     fused_v_loss(model.net, xs[0], ns[0], sg[0]).backward()
     for p, g1 in zip(model.net.parameters(), singles[0]):
-        assert float((p.grad - g1).norm()) <= 2e-3 * max(float(g1.norm()), floor)
+        assert float((p.grad - g1).norm()) <= 2e-3 * float(g1.norm()) + 2e-2 * floor
 
 
 def test_stale_plan_raises(oracle_port):
