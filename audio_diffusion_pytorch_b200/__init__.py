@@ -4,8 +4,8 @@ for the UNetV0 + VDiffusion/VSampler hot path, executed by hand-written sm_100a 
 Out-of-scope names of the reference raise on use instead of silently
 running something else."""
 from .components import AppendChannelsPlugin, MelSpectrogram, UNetV0
-from .diffusion import (Diffusion, Distribution, LinearSchedule, Sampler, Schedule,
-                        UniformDistribution, VDiffusion, VSampler)
+from .diffusion import (Diffusion, Distribution, Inpainter, LinearSchedule, Sampler, Schedule,
+                        UniformDistribution, VDiffusion, VInpainter, VSampler)
 from .models import DiffusionModel, DiffusionUpsampler, DiffusionVocoder
 from .unet import B200UNet
 
@@ -21,7 +21,6 @@ def _out_of_scope(name: str, why: str):
 
 XUNet = B200UNet
 LTPlugin = _out_of_scope("LTPlugin", "not used by any model class or config")
-VInpainter = _out_of_scope("VInpainter", "SURVEY.md 8f item 1")
 DiffusionAE = _out_of_scope("DiffusionAE", "needs the external audio_encoders_pytorch package")
 DiffusionAR = _out_of_scope("DiffusionAR", "use_modulation=False / SkipCat path, SURVEY.md 8f item 1")
 EncoderBase = _out_of_scope("EncoderBase", "DiffusionAE only")
@@ -29,4 +28,4 @@ EncoderBase = _out_of_scope("EncoderBase", "DiffusionAE only")
 __all__ = ["UNetV0", "XUNet", "LTPlugin", "MelSpectrogram", "VDiffusion", "VSampler", "VInpainter",
            "LinearSchedule", "UniformDistribution", "Diffusion", "Distribution", "Sampler",
            "Schedule", "DiffusionModel", "DiffusionUpsampler", "DiffusionVocoder", "DiffusionAE",
-           "DiffusionAR", "EncoderBase", "AppendChannelsPlugin", "B200UNet"]
+           "DiffusionAR", "EncoderBase", "AppendChannelsPlugin", "B200UNet", "Inpainter"]

@@ -22,6 +22,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
                     pack_bf16(f[6], f[7]));
 }
 
+// The streaming kernels below give every thread 8 fixed channels (c0 = (global tid % vpr) * 8,
+// vpr = C/8 vectors per row).  When vpr < 32 the lanes l, l+vpr, l+2vpr, ... of a warp own the
+// SAME channels: fold their partial sums with shuffles so that one lane per channel touches the
+// block's shared-memory bins (at C = 32 the unfolded version sent 64 threads to every bin and
+// the kernel ran at 5 % of HBM bandwidth, profiles/r2_train_profile_start.txt).
+__device__ __forceinline__ bool fold_ok(int vpr) { return vpr < 32 && (32 % vpr) == 0; }
+__device__ __forceinline__ float fold_lanes(float v, int vpr) {
+  for (int o = vpr; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // per-(batch, channel) GroupNorm coefficients -> smem: mean[c], rstd[c]
 __device__ __forceinline__ void gn_coeffs(const double* stats, int b, int T, int C, int groups,
                                           float eps, float* s_mean, float* s_rstd) {
@@ -51,11 +62,10 @@ gn_silu_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ x,
   pdl_wait();
   __shared__ float s_mean[kBwMaxC], s_rstd[kBwMaxC];
   __shared__ float s_dg[kBwMaxC], s_db[kBwMaxC];
-  __shared__ float s_S[2 * 64];
+  __shared__ float s_s1[kBwMaxC], s_s2[kBwMaxC];      // per-channel sums of dxh, dxh*xhat
   const int b = blockIdx.y;
   gn_coeffs(stats, b, T, C, groups, eps, s_mean, s_rstd);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
-  if (threadIdx.x < 128) s_S[threadIdx.x] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; s_s1[c] = 0.f; s_s2[c] = 0.f; }
   __syncthreads();
   const int gsz = C / groups;
   const int vpr = C >> 3;
@@ -99,14 +109,22 @@ gn_silu_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ x,
       as1[j] += orr[j]; as2[j] += orr[j] * xh;
     }
   }
-  if (tid < stride) {
+  {
+    const bool fold = fold_ok(vpr);
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_dg[c0 + j], adg[j]);
-      atomicAdd(&s_db[c0 + j], adb[j]);
-      const int g = (c0 + j) / gsz;
-      atomicAdd(&s_S[2 * g], as1[j]);
-      atomicAdd(&s_S[2 * g + 1], as2[j]);
+      float v0 = adg[j], v1 = adb[j], v2 = as1[j], v3 = as2[j];
+      if (fold) {
+        v0 = fold_lanes(v0, vpr); v1 = fold_lanes(v1, vpr);
+        v2 = fold_lanes(v2, vpr); v3 = fold_lanes(v3, vpr);
+      }
+      if (!fold || lane < vpr) {
+        atomicAdd(&s_dg[c0 + j], v0);
+        atomicAdd(&s_db[c0 + j], v1);
+        atomicAdd(&s_s1[c0 + j], v2);
+        atomicAdd(&s_s2[c0 + j], v3);
+      }
     }
   }
   __syncthreads();
@@ -114,9 +132,13 @@ gn_silu_bwd_kernel(const uint4* __restrict__ da, const uint4* __restrict__ x,
     atomicAdd(dgamma + c, s_dg[c]);
     atomicAdd(dbeta + c, s_db[c]);
   }
-  if (threadIdx.x < 2 * groups)
-    atomicAdd(S + static_cast<size_t>(b) * 2 * groups + threadIdx.x,
-              static_cast<double>(s_S[threadIdx.x]));
+  if (threadIdx.x < 2 * groups) {      // thread (g, which) sums its group's channels: no contention
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const float* src = which ? s_s2 : s_s1;
+    float tot = 0.f;
+    for (int c = g * gsz; c < (g + 1) * gsz; ++c) tot += src[c];
+    atomicAdd(S + static_cast<size_t>(b) * 2 * groups + threadIdx.x, static_cast<double>(tot));
+  }
 }
 
 // ---------------------------------------------------------------------- gn_bwd_apply
@@ -173,9 +195,11 @@ gn_bwd_apply_kernel(const uint4* __restrict__ dxh, const uint4* __restrict__ x,
     }
   }
   if (colsum) {
-    if (tid < stride) {
+    const bool fold = fold_ok(vpr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&s_cs[c0 + j], acs[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v = fold ? fold_lanes(acs[j], vpr) : acs[j];
+      if (!fold || (threadIdx.x & 31) < vpr) atomicAdd(&s_cs[c0 + j], v);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(colsum + c, s_cs[c]);
@@ -337,10 +361,14 @@ colsum_kernel(const uint4* __restrict__ x, const float* __restrict__ gate, int l
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += f[j];
   }
-  if (tid < stride) {
+  {
+    const bool fold = fold_ok(vpr);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      atomicAdd(&s_cs[c0 + j], gate ? acc[j] * gate[static_cast<size_t>(b) * ld_gate + c0 + j] : acc[j]);
+    for (int j = 0; j < 8; ++j) {
+      float v = gate ? acc[j] * gate[static_cast<size_t>(b) * ld_gate + c0 + j] : acc[j];
+      if (fold) v = fold_lanes(v, vpr);
+      if (!fold || (threadIdx.x & 31) < vpr) atomicAdd(&s_cs[c0 + j], v);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + c, s_cs[c]);
@@ -354,9 +382,9 @@ skip_gate_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
                  double* __restrict__ stats, int T, int C, int groups) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_S[2 * 64];
+  __shared__ float s_s1[kBwMaxC], s_s2[kBwMaxC];      // per-channel sum / sum of squares of out
   const int b = blockIdx.y;
-  if (threadIdx.x < 128) s_S[threadIdx.x] = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_s1[c] = 0.f; s_s2[c] = 0.f; }
   __syncthreads();
   const int vpr = C >> 3, gsz = groups > 0 ? C / groups : C;
   const size_t nvec = static_cast<size_t>(T) * vpr, boff = static_cast<size_t>(b) * nvec;
@@ -383,18 +411,24 @@ skip_gate_kernel(const uint4* __restrict__ y, const uint4* __restrict__ skip,
     }
   }
   if (stats) {
-    if (tid < stride) {
+    const bool fold = fold_ok(vpr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (c0 + j) / gsz;
-        atomicAdd(&s_S[2 * g], s1[j]);
-        atomicAdd(&s_S[2 * g + 1], s2[j]);
+    for (int j = 0; j < 8; ++j) {
+      float v1 = s1[j], v2 = s2[j];
+      if (fold) { v1 = fold_lanes(v1, vpr); v2 = fold_lanes(v2, vpr); }
+      if (!fold || (threadIdx.x & 31) < vpr) {
+        atomicAdd(&s_s1[c0 + j], v1);
+        atomicAdd(&s_s2[c0 + j], v2);
       }
     }
     __syncthreads();
-    if (threadIdx.x < 2 * groups)
-      atomicAdd(stats + static_cast<size_t>(b) * 2 * groups + threadIdx.x,
-                static_cast<double>(s_S[threadIdx.x]));
+    if (threadIdx.x < 2 * groups) {
+      const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+      const float* src = which ? s_s2 : s_s1;
+      float tot = 0.f;
+      for (int c = g * gsz; c < (g + 1) * gsz; ++c) tot += src[c];
+      atomicAdd(stats + static_cast<size_t>(b) * 2 * groups + threadIdx.x, static_cast<double>(tot));
+    }
   }
 }
 
@@ -426,9 +460,13 @@ skip_gate_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y
     for (int j = 0; j < 8; ++j) { o[j] = g8[j] * fd[j]; adg[j] += fd[j] * fy[j]; }
     dys[boff + i] = pack8(o);
   }
-  if (tid < stride) {
+  {
+    const bool fold = fold_ok(vpr);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_dg[c0 + j], adg[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v = fold ? fold_lanes(adg[j], vpr) : adg[j];
+      if (!fold || (threadIdx.x & 31) < vpr) atomicAdd(&s_dg[c0 + j], v);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x)
@@ -437,9 +475,11 @@ skip_gate_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y
 
 // -------------------------------------------------------------------------- cond_bwd
 // ss[b][n] = sum_k cond[b][k] * W[n][k] + bias[n]:
-//   dW[n][k] = sum_b dss[b][n]*cond[b][k],  dbias[n] = sum_b dss[b][n]   (grid.y == 0 part)
+//   dW[n][k] = sum_b dss[b][n]*cond[b][k],  dbias[n] = sum_b dss[b][n]
 //   dcond[b][k] += sum_n dss[b][n]*W[n][k]
-constexpr int kCondMaxB = 32;
+// Pure streaming (W read once as bf16, dW written once as fp32): every thread owns 4 consecutive
+// k, so W arrives as 8-byte and dW leaves as 16-byte vectors; cond[.][k..k+3] stays in registers.
+constexpr int kCondMaxB = 8;          // batch rows per pass (the launcher loops over larger batches)
 __global__ void __launch_bounds__(256)
 cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restrict__ cond,
                 const __nv_bfloat16* __restrict__ w, float* __restrict__ dw,
@@ -447,15 +487,12 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
                 int rows_per_block, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_buf[];     // cond [B][K], then dss slab [B][rows_per_block]
-  float* s_cond = s_buf;
-  float* s_d = s_buf + B * K;
+  extern __shared__ float s_d[];       // dss slab [B][rows_per_block]
   const int n0 = blockIdx.x * rows_per_block;
   const int nr = min(rows_per_block, N - n0);
-  for (int i = threadIdx.x; i < B * K; i += blockDim.x) s_cond[i] = cond[i];
-  for (int i = threadIdx.x; i < B * rows_per_block; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kCondMaxB * rows_per_block; i += blockDim.x) {
     const int bb = i / rows_per_block, r = i - bb * rows_per_block;
-    s_d[i] = r < nr ? dss[static_cast<size_t>(bb) * ld_dss + n0 + r] : 0.f;
+    s_d[i] = (bb < B && r < nr) ? dss[static_cast<size_t>(bb) * ld_dss + n0 + r] : 0.f;
   }
   __syncthreads();
   if (threadIdx.x < nr) {
@@ -463,33 +500,46 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
     for (int bb = 0; bb < B; ++bb) t += s_d[bb * rows_per_block + threadIdx.x];
     dbias[n0 + threadIdx.x] = accumulate ? dbias[n0 + threadIdx.x] + t : t;
   }
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float dc[kCondMaxB];
+  for (int k4 = threadIdx.x * 4; k4 < K; k4 += blockDim.x * 4) {
+    float4 c4[kCondMaxB], dc[kCondMaxB];
 #pragma unroll
-    for (int bb = 0; bb < kCondMaxB; ++bb) dc[bb] = 0.f;
+    for (int bb = 0; bb < kCondMaxB; ++bb) {
+      c4[bb] = bb < B ? *reinterpret_cast<const float4*>(cond + static_cast<size_t>(bb) * K + k4)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      dc[bb] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll 4
     for (int r = 0; r < nr; ++r) {
-      const float wv = __bfloat162float(w[static_cast<size_t>(n0 + r) * K + k]);
-      float g = 0.f;
+      const uint2 wu = __ldg(reinterpret_cast<const uint2*>(w + static_cast<size_t>(n0 + r) * K + k4));
+      const float2 w01 = unpack_bf16(wu.x), w23 = unpack_bf16(wu.y);
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int bb = 0; bb < kCondMaxB; ++bb) {
-        if (bb < B) {
-          const float d = s_d[bb * rows_per_block + r];
-          g += d * s_cond[bb * K + k];
-          dc[bb] += d * wv;
-        }
+        const float d = s_d[bb * rows_per_block + r];       // zero rows beyond B: no branch needed
+        g.x += d * c4[bb].x; g.y += d * c4[bb].y; g.z += d * c4[bb].z; g.w += d * c4[bb].w;
+        dc[bb].x += d * w01.x; dc[bb].y += d * w01.y; dc[bb].z += d * w23.x; dc[bb].w += d * w23.y;
       }
-      float* dwp = dw + static_cast<size_t>(n0 + r) * K + k;
-      *dwp = accumulate ? *dwp + g : g;
+      float4* dwp = reinterpret_cast<float4*>(dw + static_cast<size_t>(n0 + r) * K + k4);
+      if (accumulate) {
+        const float4 o = *dwp;
+        g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+      }
+      *dwp = g;
     }
 #pragma unroll
     for (int bb = 0; bb < kCondMaxB; ++bb)
-      if (bb < B) atomicAdd(dcond + static_cast<size_t>(bb) * K + k, dc[bb]);
+      if (bb < B) {
+        float* dp = dcond + static_cast<size_t>(bb) * K + k4;
+        atomicAdd(dp, dc[bb].x); atomicAdd(dp + 1, dc[bb].y);
+        atomicAdd(dp + 2, dc[bb].z); atomicAdd(dp + 3, dc[bb].w);
+      }
   }
 }
 
 static int grid_for(size_t nvec, int B) {
-  size_t g = (nvec + 256 * 2 - 1) / (256 * 2);
-  const size_t cap = 148 * 8 / (B < 8 ? B : 8) + 1;
+  // every block ends in 2C global atomics: a few hundred blocks in total, each streaming many rows
+  size_t g = (nvec + 256 * 4 - 1) / (256 * 4);
+  const size_t cap = 148 * 3 / (B < 8 ? B : 8) + 1;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return static_cast<int>(g);
@@ -543,8 +593,11 @@ extern "C" int adp_ln_film_bwd(const void* dy, const void* x, const float* scale
     lpr = 32; vpl = vpr / 32;
   }
   const int rows_per_block = 8 * (32 / lpr);
-  size_t g = (static_cast<size_t>(T) + rows_per_block * 4 - 1) / (rows_per_block * 4);
-  const size_t cap = 148 * 8 / (B < 8 ? B : 8) + 1;
+  // few rows (deep levels): one pass per warp so that every SM gets a block; many rows: persistent
+  // blocks (each ends in 3C global atomics)
+  const size_t g1 = (static_cast<size_t>(T) + rows_per_block - 1) / rows_per_block;
+  size_t g = g1 * B <= 148 * 2 ? g1 : (static_cast<size_t>(T) + rows_per_block * 4 - 1) / (rows_per_block * 4);
+  const size_t cap = 148 * 4 / (B < 8 ? B : 8) + 1;
   if (g > cap) g = cap;
   dim3 grid(static_cast<unsigned>(g < 1 ? 1 : g), B);
   const uint4* pdy = static_cast<const uint4*>(dy);
@@ -576,7 +629,7 @@ extern "C" int adp_skip_gate(const void* y, const void* skip, const float* gate,
                              void* out, double* stats, int32_t B, int32_t T, int32_t C,
                              int32_t groups, adp_stream_t stream) {
   ADP_CHECK(y && skip && gate && out && C % 8 == 0, "adp_skip_gate: bad args");
-  ADP_CHECK(!stats || (groups > 0 && groups <= 64 && C % groups == 0), "adp_skip_gate: groups");
+  ADP_CHECK(!stats || (groups > 0 && groups <= 64 && C % groups == 0 && C <= kBwMaxC), "adp_skip_gate: groups");
   dim3 grid(grid_for(static_cast<size_t>(T) * (C / 8), B), B);
   ADP_CUDA(launch_k(skip_gate_kernel, grid, dim3(256), (size_t)0, as_stream(stream),
                     static_cast<const uint4*>(y), static_cast<const uint4*>(skip), gate,
@@ -604,9 +657,10 @@ extern "C" int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond,
   static SmemAttrCache smem_cache;
   dim3 grid((N + rows_per_block - 1) / rows_per_block);
   // batches beyond kCondMaxB rows run as further passes that accumulate into dw / dbias
+  ADP_CHECK(K % 4 == 0, "adp_cond_bwd: K=%d must be a multiple of 4", K);
   for (int b0 = 0; b0 < B; b0 += kCondMaxB) {
     const int bc = B - b0 < kCondMaxB ? B - b0 : kCondMaxB;
-    const size_t smem = (static_cast<size_t>(bc) * K + static_cast<size_t>(bc) * rows_per_block) * sizeof(float);
+    const size_t smem = static_cast<size_t>(kCondMaxB) * rows_per_block * sizeof(float);
     ADP_CUDA(ensure_dyn_smem(cond_bwd_kernel, smem, smem_cache));
     ADP_CUDA(launch_k(cond_bwd_kernel, grid, dim3(256), smem, as_stream(stream),
                       dss + static_cast<size_t>(b0) * ld_dss, (int)ld_dss,

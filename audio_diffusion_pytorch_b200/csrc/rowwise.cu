@@ -330,12 +330,28 @@ ln_film_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* 
           atomicAdd(&s_acc[2 * g], as[j]);
           atomicAdd(&s_acc[2 * g + 1], aq[j]);
         }
-      } else {
+      }
+    }
+    if constexpr (!PER_CH) {
+      // gsz/8 consecutive lanes of a row hold channels of the SAME group: reduce them with
+      // shuffles so that one lane per (warp, group) touches the 2*groups shared bins (at
+      // C = 1024 the per-lane version queued 16 lanes on every bin and tripled the kernel time)
+      const int lpg = gsz >> 3;                               // lanes (vectors) per group
+      const int span = lpg < lpr ? lpg : lpr;                 // lanes to fold
+      const bool tree = span > 0 && (span & (span - 1)) == 0 && (lpg >= lpr ? lpg % lpr == 0 : lpr % lpg == 0);
 #pragma unroll
-        for (int it = 0; it < VPL; ++it) {
+      for (int it = 0; it < VPL; ++it) {
+        float sa = as[it], sq = aq[it];
+        if (tree) {
+          for (int o = span >> 1; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+        }
+        if (sub == 0 && (!tree || (l & (span - 1)) == 0)) {
           const int g = ((it * lpr + l) << 3) / gsz;
-          atomicAdd(&s_acc[2 * g], as[it]);
-          atomicAdd(&s_acc[2 * g + 1], aq[it]);
+          atomicAdd(&s_acc[2 * g], sa);
+          atomicAdd(&s_acc[2 * g + 1], sq);
         }
       }
     }
@@ -444,6 +460,19 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
     const float n_pred = b0 * xv + a0 * vv;   // :186
     xn[i] = a1 * x_pred + b1 * n_pred;        // :187
   }
+}
+
+// VInpainter (reference diffusion.py:349-350): where mask, x := a1*source + b1*noise (the known
+// region re-noised to the level the sampler just stepped to); elsewhere x keeps the sampler's value
+__global__ void inpaint_blend_kernel(float* __restrict__ x, const float* __restrict__ source,
+                                     const float* __restrict__ noise, const uint8_t* __restrict__ mask,
+                                     const float* __restrict__ ab, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float a1 = ab[2], b1 = ab[3];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (mask[i]) x[i] = a1 * source[i] + b1 * noise[i];
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -590,6 +619,15 @@ extern "C" int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t st
   ADP_CHECK(x && y && n > 0, "adp_silu_bf16: bad args");
   ADP_CUDA(launch_k(silu_bf16_kernel, dim3(pick_grid(static_cast<size_t>(n), 256, 148 * 4)),
                     dim3(256), (size_t)0, as_stream(stream), x, static_cast<__nv_bfloat16*>(y), n));
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_inpaint_blend(float* x, const float* source, const float* noise, const uint8_t* mask,
+                                 const float* ab, int64_t n, adp_stream_t stream) {
+  ADP_CHECK(x && source && noise && mask && ab && n > 0, "adp_inpaint_blend: bad args");
+  ADP_CUDA(launch_k(inpaint_blend_kernel, dim3(pick_grid(static_cast<size_t>(n), 256 * 4, 148 * 8)),
+                    dim3(256), (size_t)0, as_stream(stream), x, source, noise, mask, ab, n));
   ADP_LAUNCH_CHECK();
   return 0;
 }

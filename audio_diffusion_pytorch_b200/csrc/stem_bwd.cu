@@ -9,6 +9,13 @@ namespace adp {
 
 constexpr int kTB = 256;
 
+// blocks per batch element for the persistent tile loops: ~4 blocks per SM in total
+static int persistent_blocks(int n_tiles, int B) {
+  int g = (148 * 4 + B - 1) / B;
+  if (g > n_tiles) g = n_tiles;
+  return g < 1 ? 1 : g;
+}
+
 // ---------------------------------------------------------------------- narrow_conv_bwd
 // forward: y = conv3(a) + bias, a = silu(xhat*gamma + beta), C == 8.  Given dy:
 //   dxh = (conv3^T dy) * silu'(z) * gamma  (first GroupNorm-backward pass, see adp_gn_bwd_apply)
@@ -24,7 +31,11 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
   __shared__ float s_ga[C], s_be[C], s_mean[C], s_rstd[C];
   __shared__ float s_red[4 * C];                        // dgamma, dbeta, S1, S2 per channel
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kTB;
+  // persistent over row tiles: the parameter gradients stay in registers / smem and reach global
+  // memory with ONE atomic per parameter per block (one block per tile meant 4096 same-address
+  // atomics per parameter and a 130 us kernel, profiles/r2_train_profile_start.txt)
+  const int n_tiles = (a.T + kTB - 1) / kTB;
+  float acc_w = 0.f;                                   // this thread's dw / dbias element
   for (int i = threadIdx.x; i < 3 * C * C; i += kTB) {
     const int k = i / (C * C), r = i - k * C * C, co = r / C, ci = r - co * C;
     s_w[i] = a.w[(co * C + ci) * 3 + k];
@@ -44,6 +55,9 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
   __syncthreads();
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(a.x) + static_cast<size_t>(b) * a.T * C;
   const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(a.dy) + static_cast<size_t>(b) * a.T * C;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int t0 = tile * kTB;
+  __syncthreads();                                     // previous tile's smem fully consumed
   for (int i = threadIdx.x; i < kTB + 2; i += kTB) {
     const int t = t0 - 1 + i;
 #pragma unroll
@@ -121,13 +135,16 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
     const int co = threadIdx.x / (3 * C), r = threadIdx.x - co * 3 * C, ci = r / 3, k = r - ci * 3;
     float acc = 0.f;
     for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co] * s_a[(i + k) * C + ci];
-    atomicAdd(a.dw + threadIdx.x, acc);           // PyTorch layout [co][ci][k]
+    acc_w += acc;
   } else if (threadIdx.x < 3 * C * C + C) {
     const int co = threadIdx.x - 3 * C * C;
     float acc = 0.f;
     for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co];
-    atomicAdd(a.dbias + co, acc);
+    acc_w += acc;
   }
+  }  // tiles
+  if (threadIdx.x < 3 * C * C) atomicAdd(a.dw + threadIdx.x, acc_w);           // PyTorch layout [co][ci][k]
+  else if (threadIdx.x < 3 * C * C + C) atomicAdd(a.dbias + (threadIdx.x - 3 * C * C), acc_w);
   __syncthreads();
   if (threadIdx.x < C) {
     atomicAdd(a.dgamma + threadIdx.x, s_red[threadIdx.x]);
@@ -144,6 +161,7 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
 // ------------------------------------------------------------------------- stem_out_bwd
 constexpr int kSoMaxC0 = 64;
 constexpr int kSoMaxCo = 4;
+constexpr int kSoItems = 4;      // parameter-gradient elements per thread (co*c0*3 + ... <= 1024)
 __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bwd_args a) {
   pdl_launch_dependents();
   pdl_wait();
@@ -156,15 +174,25 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
   float* s_dv = s_dy + (kTB + 2) * a.co;            // [TB][co]      = dv * gscale
   float* s_xin = s_dv + kTB * a.co;                 // [TB][cin]
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kTB;                  // multiple of f (TB % f == 0)
   const int Tl = a.T / a.f;
-  const int q0 = t0 / a.f - 1;                      // first low-res row held in s_h
   const int ldg = a.ld_gate > 0 ? a.ld_gate : a.co;
   const float gscale = a.gscale ? a.gscale[0] : 1.f;
   for (int i = threadIdx.x; i < a.co * 3 * a.c0; i += kTB) {
     const int o = i / (3 * a.c0), r = i - o * 3 * a.c0, k = r / a.c0, c = r - k * a.c0;
     s_w[i] = a.w[(o * a.c0 + c) * 3 + k];
   }
+  // persistent over tiles; each thread owns up to kSoItems parameter-gradient elements and adds
+  // them to global memory once per block (see adp_narrow_conv_bwd)
+  float acc_it[kSoItems];
+#pragma unroll
+  for (int k = 0; k < kSoItems; ++k) acc_it[k] = 0.f;
+  const int n_tiles = (a.T + kTB - 1) / kTB;
+  const int n_w = a.co * a.c0 * 3, n_ad = a.w_adapt ? a.co * cin : 0;
+  const int n_items = n_w + a.co /*bias*/ + a.co /*gate*/ + n_ad + (a.w_adapt ? a.co : 0);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int t0 = tile * kTB;                        // multiple of f (TB % f == 0)
+  const int q0 = t0 / a.f - 1;                      // first low-res row held in s_h
+  __syncthreads();                                  // previous tile's smem fully consumed
   const __nv_bfloat16* hb = static_cast<const __nv_bfloat16*>(a.h) + static_cast<size_t>(b) * Tl * a.c0;
   for (int i = threadIdx.x; i < rows_h * a.c0; i += kTB) {
     const int r = i / a.c0, c = i - r * a.c0, q = q0 + r;
@@ -227,9 +255,10 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
     }
   }
   // (2) parameter gradients: flat work items, one dot product over the tile each
-  const int n_w = a.co * a.c0 * 3, n_ad = a.w_adapt ? a.co * cin : 0;
-  const int n_items = n_w + a.co /*bias*/ + a.co /*gate*/ + n_ad + (a.w_adapt ? a.co : 0);
-  for (int item = threadIdx.x; item < n_items; item += kTB) {
+#pragma unroll
+  for (int kk = 0; kk < kSoItems; ++kk) {
+    const int item = threadIdx.x + kk * kTB;
+    if (item >= n_items) break;
     float acc = 0.f;
     if (item < n_w) {                         // dw[co][c0][k] (PyTorch layout)
       const int o = item / (a.c0 * 3), r = item - o * a.c0 * 3, c = r / 3, k = r - c * 3;
@@ -238,11 +267,9 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
         if (u < 0 || u >= a.T) continue;
         acc += s_dy[(i + 1) * a.co + o] * s_h[(u / a.f - q0) * a.c0 + c];
       }
-      atomicAdd(a.dw + item, acc);
     } else if (item < n_w + a.co) {           // dbias
       const int o = item - n_w;
       for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * a.co + o];
-      atomicAdd(a.dbias + o, acc);
     } else if (item < n_w + 2 * a.co) {       // dgate[b][o] = sum dv * y,  y = conv(hup) + bias
       const int o = item - n_w - a.co;
       const float bo = a.bias ? a.bias[o] : 0.f;
@@ -257,16 +284,14 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
         }
         acc += s_dv[i * a.co + o] * y;
       }
-      atomicAdd(a.dgate + static_cast<size_t>(b) * a.ld_dgate + o, acc);
     } else if (item < n_w + 2 * a.co + n_ad) {   // SkipAdapter weight [co][cin]
       const int r = item - n_w - 2 * a.co, o = r / cin, c = r - o * cin;
       for (int i = 0; i < nvalid; ++i) acc += s_dv[i * a.co + o] * s_xin[i * cin + c];
-      atomicAdd(a.dw_adapt + r, acc);
     } else {                                      // SkipAdapter bias
       const int o = item - n_w - 2 * a.co - n_ad;
       for (int i = 0; i < nvalid; ++i) acc += s_dv[i * a.co + o];
-      atomicAdd(a.db_adapt + o, acc);
     }
+    acc_it[kk] += acc;
   }
   // (3) gradient w.r.t. the net input through the skip path (v = skip(x_in) + gate*y):
   // identity skip -> dv, SkipAdapter -> W_adapt^T dv.  Plain stores: adp_stem_in_bwd adds the
@@ -284,9 +309,23 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
       a.dxin[(static_cast<size_t>(b) * cin + c) * a.T + t0 + r] = acc;
     }
   }
+  }  // tiles
+#pragma unroll
+  for (int kk = 0; kk < kSoItems; ++kk) {
+    const int item = threadIdx.x + kk * kTB;
+    if (item >= n_items) break;
+    const float acc = acc_it[kk];
+    if (item < n_w) atomicAdd(a.dw + item, acc);
+    else if (item < n_w + a.co) atomicAdd(a.dbias + (item - n_w), acc);
+    else if (item < n_w + 2 * a.co)
+      atomicAdd(a.dgate + static_cast<size_t>(b) * a.ld_dgate + (item - n_w - a.co), acc);
+    else if (item < n_w + 2 * a.co + n_ad) atomicAdd(a.dw_adapt + (item - n_w - 2 * a.co), acc);
+    else atomicAdd(a.db_adapt + (item - n_w - 2 * a.co - n_ad), acc);
+  }
 }
 
 // -------------------------------------------------------------------------- stem_in_bwd
+constexpr int kSiItems = 9;      // c0 * (cx+ca) * f + c0 <= 64*32 + 64 parameter-gradient elements
 __global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_args a) {
   pdl_launch_dependents();
   pdl_wait();
@@ -296,9 +335,16 @@ __global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_
   float* s_g = s_in + kTB * ci_total;       // [TB][c0]
   const int b = blockIdx.y;
   const int To = a.T / a.f;
-  const int to0 = blockIdx.x * kTB;
   float al = 1.f, be = 0.f;
   if (a.noise) { al = a.alpha[b]; be = a.beta[b]; }
+  const int n_w = a.c0 * ci_total;
+  float acc_it[kSiItems];          // persistent blocks: parameter gradients flushed once per block
+#pragma unroll
+  for (int k = 0; k < kSiItems; ++k) acc_it[k] = 0.f;
+  const int n_tiles = (To + kTB - 1) / kTB;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int to0 = tile * kTB;
+  __syncthreads();
   for (int i = threadIdx.x; i < kTB * ci_total; i += kTB) {
     const int r = i / ci_total, ii = i - r * ci_total, c = ii / a.f, j = ii - c * a.f, to = to0 + r;
     float v = 0.f;
@@ -320,18 +366,19 @@ __global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_
     s_g[i] = to < To ? __bfloat162float(gb[static_cast<size_t>(to) * a.c0 + (i - r * a.c0)]) : 0.f;
   }
   __syncthreads();
-  const int n_w = a.c0 * ci_total;
-  for (int item = threadIdx.x; item < n_w + a.c0; item += kTB) {
+#pragma unroll
+  for (int kk = 0; kk < kSiItems; ++kk) {
+    const int item = threadIdx.x + kk * kTB;
+    if (item >= n_w + a.c0) break;
     float acc = 0.f;
     if (item < n_w) {                        // dw[c0][cin][f] flat == [c0][ci_total]
       const int o = item / ci_total, ii = item - o * ci_total;
       for (int i = 0; i < kTB; ++i) acc += s_g[i * a.c0 + o] * s_in[i * ci_total + ii];
-      atomicAdd(a.dw + item, acc);
     } else {
       const int o = item - n_w;
       for (int i = 0; i < kTB; ++i) acc += s_g[i * a.c0 + o];
-      atomicAdd(a.dbias + o, acc);
     }
+    acc_it[kk] += acc;
   }
   // gradient w.r.t. cat([x, append]) through the k = s = f DownsampleItem, ADDED to what
   // adp_stem_out_bwd stored: dxin[b][c][to*f + j] += sum_o dout[b][to][o] * w[o][c][j]
@@ -346,6 +393,14 @@ __global__ void __launch_bounds__(kTB) stem_in_bwd_kernel(const adp_stem_in_bwd_
       a.dxin[(static_cast<size_t>(b) * cin + c) * a.T + static_cast<size_t>(to) * a.f + j] += acc;
     }
   }
+  }  // tiles
+#pragma unroll
+  for (int kk = 0; kk < kSiItems; ++kk) {
+    const int item = threadIdx.x + kk * kTB;
+    if (item >= n_w + a.c0) break;
+    if (item < n_w) atomicAdd(a.dw + item, acc_it[kk]);
+    else atomicAdd(a.dbias + (item - n_w), acc_it[kk]);
+  }
 }
 
 }  // namespace adp
@@ -358,7 +413,7 @@ extern "C" int adp_narrow_conv_bwd(const adp_narrow_conv_bwd_args* args, adp_str
             "adp_narrow_conv_bwd: null pointer");
   const adp_narrow_conv_bwd_args& a = *args;
   ADP_CHECK(a.C == 8 && a.groups > 0 && a.C % a.groups == 0, "adp_narrow_conv_bwd: C=%d groups=%d", a.C, a.groups);
-  dim3 grid((a.T + kTB - 1) / kTB, a.B);
+  dim3 grid(persistent_blocks((a.T + kTB - 1) / kTB, a.B), a.B);
   ADP_CUDA(launch_k(narrow_conv_bwd_kernel<8>, grid, dim3(kTB), (size_t)0, as_stream(stream), a));
   return 0;
 }
@@ -378,7 +433,8 @@ extern "C" int adp_stem_out_bwd(const adp_stem_out_bwd_args* args, adp_stream_t 
                        static_cast<size_t>(kTB) * cin) * sizeof(float);
   static SmemAttrCache smem_cache;
   ADP_CUDA(ensure_dyn_smem(stem_out_bwd_kernel, smem, smem_cache));
-  dim3 grid((a.T + kTB - 1) / kTB, a.B);
+  ADP_CHECK(a.co * a.c0 * 3 + 3 * a.co + a.co * cin <= kSoItems * kTB, "adp_stem_out_bwd: too many parameters");
+  dim3 grid(persistent_blocks((a.T + kTB - 1) / kTB, a.B), a.B);
   ADP_CUDA(launch_k(stem_out_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
   return 0;
 }
@@ -393,7 +449,7 @@ extern "C" int adp_stem_in_bwd(const adp_stem_in_bwd_args* args, adp_stream_t st
   const size_t smem = (static_cast<size_t>(kTB) * (a.cx + a.ca) * a.f + static_cast<size_t>(kTB) * a.c0) * sizeof(float);
   static SmemAttrCache smem_cache;
   ADP_CUDA(ensure_dyn_smem(stem_in_bwd_kernel, smem, smem_cache));
-  dim3 grid((a.T / a.f + kTB - 1) / kTB, a.B);
+  dim3 grid(persistent_blocks((a.T / a.f + kTB - 1) / kTB, a.B), a.B);
   ADP_CUDA(launch_k(stem_in_bwd_kernel, grid, dim3(kTB), smem, as_stream(stream), a));
   return 0;
 }

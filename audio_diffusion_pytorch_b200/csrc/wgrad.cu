@@ -21,6 +21,7 @@ constexpr int kWgMaxStages = 8;
 
 struct WgradParams {
   float* dw;
+  long long tap_stride;    // floats between the dW slabs of consecutive taps (fused 3-tap mode)
   int ldw;                 // row pitch of dW in floats
   int n_valid, k_valid;    // real out / in channel counts (tile masks)
   int T, chunks_per_batch, total_chunks, chunks_per_split;
@@ -28,12 +29,19 @@ struct WgradParams {
   int n_stages, nb;        // nb = BN / 64 boxes of X per stage
 };
 
-template <int BN>
+// NT = 3: the three taps of a k=3 convolution in ONE launch.  The X box carries 2 extra time rows;
+// tap j is the same smem tile read through a descriptor whose start is advanced by j rows (the
+// 128-byte swizzle is a function of the absolute address, as for the shifted-tap forward GEMM), and
+// accumulates into its own TMEM columns.  G and X are read once instead of three times.
+template <int BN, int NT>
 __global__ void __launch_bounds__(192, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
              const WgradParams p) {
   constexpr int NB = BN / 64;
-  constexpr int STAGE_BYTES = (2 + NB) * kWgBoxBytes;
+  constexpr int XBOX = NT == 1 ? kWgBoxBytes : 9 * 1024;        // (64 + NT - 1) rows x 128 B, 1 KB-rounded
+  constexpr int STAGE_BYTES = 2 * kWgBoxBytes + NB * XBOX;
+  constexpr int TCOLS = NT * BN <= 32 ? 32 : (NT * BN <= 64 ? 64 : (NT * BN <= 128 ? 128 : (NT * BN <= 256 ? 256 : 512)));
+  static_assert(NT * BN <= 512, "accumulators of all taps must fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages];
   __shared__ uint64_t acc_full;
@@ -52,7 +60,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   if (chunk_end > p.total_chunks) chunk_end = p.total_chunks;
 
   if (warp == 0) {
-    tmem_alloc(&tmem_slot, BN < 32 ? 32 : BN);
+    tmem_alloc(&tmem_slot, TCOLS);
     tmem_relinquish();
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -77,12 +85,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* st = ring + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        // bytes actually written: the X boxes are (64 + NT - 1) rows of 128 B (the stage slot is
+        // rounded up to 1 KB)
+        mbar_arrive_expect_tx(&full_bar[s], 2 * kWgBoxBytes + NB * (kWgChunk + NT - 1) * 128);
         tma_load_3d(st, &tmG, &full_bar[s], p.g_col0 + n0, t0, b);
         tma_load_3d(st + kWgBoxBytes, &tmG, &full_bar[s], p.g_col0 + n0 + 64, t0, b);
 #pragma unroll
         for (int i = 0; i < NB; ++i)
-          tma_load_3d(st + (2 + i) * kWgBoxBytes, &tmX, &full_bar[s], p.x_col0 + k0 + i * 64,
+          tma_load_3d(st + 2 * kWgBoxBytes + i * XBOX, &tmX, &full_bar[s], p.x_col0 + k0 + i * 64,
                       t0 + p.off, b);
       }
       __syncwarp();
@@ -92,6 +102,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
     // MN-major SW128: 64-channel chunks kWgBoxBytes apart (LBO), 8-row groups 1024 B (SBO)
     const uint64_t desc0 = umma_desc_mnmajor_sw128(smem_u32(ring), kWgBoxBytes);
+    const uint64_t xdesc0 = umma_desc_mnmajor_sw128(smem_u32(ring) + 2 * kWgBoxBytes, XBOX);
     int s = 0;
     uint32_t ph = 0, accumulate = 0;
     for (int c = chunk_begin; c < chunk_end; ++c) {
@@ -99,11 +110,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       tc_fence_after();
       if (elect_one()) {
         const uint64_t gdesc = desc0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
-        const uint64_t xdesc = gdesc + ((2 * kWgBoxBytes) >> 4);
+        const uint64_t xdesc = xdesc0 + static_cast<uint64_t>((s * STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int kk = 0; kk < kWgChunk / 16; ++kk) {      // 16 time steps per MMA = 2048 B
-          umma_bf16(tmem_base, gdesc + ((kk * 2048) >> 4), xdesc + ((kk * 2048) >> 4), idesc,
-                    accumulate | (kk != 0));
+        for (int tap = 0; tap < NT; ++tap) {
+#pragma unroll
+          for (int kk = 0; kk < kWgChunk / 16; ++kk) {      // 16 time steps per MMA = 2048 B
+            umma_bf16(tmem_base + tap * BN, gdesc + ((kk * 2048) >> 4),
+                      xdesc + ((tap * 128 + kk * 2048) >> 4), idesc, accumulate | (kk != 0));
+          }
         }
         umma_commit(&empty_bar[s]);
         if (c == chunk_end - 1) umma_commit(&acc_full);
@@ -120,11 +134,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;           // this thread's out channel (TMEM lane)
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float* drow = p.dw + static_cast<size_t>(n < p.n_valid ? n : 0) * p.ldw;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int tc = 0; tc < NT * BN; tc += 32) {
+      const int tap = tc / BN, c0 = tc - tap * BN;
+      float* drow = p.dw + tap * p.tap_stride + static_cast<size_t>(n < p.n_valid ? n : 0) * p.ldw;
       uint32_t r[32];
-      tmem_ld32(taddr + c0, r);
+      tmem_ld32(taddr + tc, r);
       tmem_ld_wait();
       if (n < p.n_valid && chunk_end > chunk_begin) {
         if (gridDim.z == 1 && k0 + c0 + 32 <= p.k_valid && (p.ldw & 3) == 0) {
@@ -148,16 +163,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, TCOLS);
   }
 }
 
-template <int BN>
+template <int BN, int NT>
 static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   constexpr int NB = BN / 64;
-  constexpr int STAGE_BYTES = (2 + NB) * kWgBoxBytes;
+  constexpr int XBOX = NT == 1 ? kWgBoxBytes : 9 * 1024;
+  constexpr int STAGE_BYTES = 2 * kWgBoxBytes + NB * XBOX;
   CUtensorMap tmG, tmX;
   const uint32_t box[3] = {64, (uint32_t)kWgChunk, 1};
+  const uint32_t xbox[3] = {64, (uint32_t)(kWgChunk + NT - 1), 1};
   {
     const uint64_t dims[3] = {(uint64_t)a.g_cols, (uint64_t)a.T, (uint64_t)a.B};
     const uint64_t str[2] = {(uint64_t)a.ldg * 2, (uint64_t)a.T * a.ldg * 2};
@@ -166,10 +183,11 @@ static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   {
     const uint64_t dims[3] = {(uint64_t)a.x_cols, (uint64_t)a.T, (uint64_t)a.B};
     const uint64_t str[2] = {(uint64_t)a.ldx * 2, (uint64_t)a.T * a.ldx * 2};
-    if (int e = make_tmap_bf16(&tmX, a.x, 3, dims, str, box, 128)) return e;
+    if (int e = make_tmap_bf16(&tmX, a.x, 3, dims, str, xbox, 128)) return e;
   }
   WgradParams p;
   p.dw = a.dw;
+  p.tap_stride = a.tap_stride;
   p.ldw = a.ldw;
   p.n_valid = a.n;
   p.k_valid = a.k;
@@ -195,9 +213,9 @@ static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   const size_t smem = static_cast<size_t>(n_stages) * STAGE_BYTES + 1024;
   static SmemAttrCache smem_cache;
-  ADP_CUDA(ensure_dyn_smem(wgrad_kernel<BN>, smem, smem_cache));
+  ADP_CUDA(ensure_dyn_smem(wgrad_kernel<BN, NT>, smem, smem_cache));
   dim3 grid(n_tiles, k_tiles, splits);
-  ADP_CUDA(launch_k(wgrad_kernel<BN>, grid, dim3(192), smem, stream, tmG, tmX, p));
+  ADP_CUDA(launch_k(wgrad_kernel<BN, NT>, grid, dim3(192), smem, stream, tmG, tmX, p));
   return 0;
 }
 
@@ -212,8 +230,14 @@ extern "C" int adp_wgrad(const adp_wgrad_args* args, adp_stream_t stream) {
             "adp_wgrad: pitches / extents must be multiples of 8");
   ADP_CHECK(a.g_col0 % 8 == 0 && a.x_col0 % 8 == 0, "adp_wgrad: column offsets must be multiples of 8");
   ADP_CHECK(a.g_col0 + a.n <= a.g_cols && a.x_col0 + a.k <= a.x_cols, "adp_wgrad: columns out of range");
+  ADP_CHECK(a.ntaps == 0 || a.ntaps == 1 || a.ntaps == 3, "adp_wgrad: ntaps must be 1 or 3");
   cudaStream_t s = as_stream(stream);
-  if (a.k > 128) return launch_wgrad<256>(a, s);
-  if (a.k > 64) return launch_wgrad<128>(a, s);
-  return launch_wgrad<64>(a, s);
+  if (a.ntaps == 3) {        // all taps of a k=3 conv: three accumulators of <= 128 columns in TMEM
+    ADP_CHECK(a.tap_stride >= (long long)a.n * a.ldw, "adp_wgrad: tap_stride smaller than one dW slab");
+    if (a.k > 64) return launch_wgrad<128, 3>(a, s);
+    return launch_wgrad<64, 3>(a, s);
+  }
+  if (a.k > 128) return launch_wgrad<256, 1>(a, s);
+  if (a.k > 64) return launch_wgrad<128, 1>(a, s);
+  return launch_wgrad<64, 1>(a, s);
 }

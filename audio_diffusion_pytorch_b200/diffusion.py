@@ -105,6 +105,61 @@ class VDiffusion(Diffusion):
         return self.loss_fn(v_pred, v_target)                                     # :95
 
 
+class Inpainter(nn.Module):
+    pass
+
+
+class VInpainter(Inpainter):
+    """reference diffusion.py:306-354: sampling with a known region.  `mask` (bool, True = keep
+    `source`) selects what is replaced, after every net evaluation, by the source noised to the
+    current level; `num_resamples` evaluations per step (RePaint-style)."""
+
+    diffusion_types = [VDiffusion]
+
+    def __init__(self, net: nn.Module, schedule: "Schedule" = None):
+        super().__init__()
+        self.net = net
+        self.schedule = LinearSchedule() if schedule is None else schedule
+
+    def get_alpha_beta(self, sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+        return _alpha_beta(sigmas)
+
+    @torch.no_grad()
+    def forward(self, source: Tensor, mask: Tensor, num_steps: int, num_resamples: int,
+                show_progress: bool = False, x_noisy: Optional[Tensor] = None, **kwargs) -> Tensor:
+        x_noisy = torch.randn_like(source) if x_noisy is None else x_noisy            # :331
+        b = x_noisy.shape[0]
+        sigmas_1d = self.schedule(num_steps + 1, device=x_noisy.device)              # :333
+        sigmas = sigmas_1d[:, None].expand(-1, b)
+        alphas, betas = _alpha_beta(sigmas_1d)
+        host_sig = sigmas_1d.tolist() if show_progress else None
+        bar = tqdm(range(num_steps), disable=not show_progress)
+
+        def progress():
+            for i in bar:
+                yield i
+                if host_sig is not None:
+                    bar.set_description(f"Inpainting (noise={host_sig[i + 1]:.2f})")
+
+        net = _inner_b200(self.net)
+        if net is not None:
+            return net.inpaint_loop(x_noisy, source, mask, sigmas, alphas, betas, num_resamples,
+                                    progress=progress(), **kwargs)
+        x = x_noisy.float().contiguous().clone()
+        src = source.float().expand_as(x).contiguous()
+        mask_u8 = mask.expand_as(x).to(torch.uint8).contiguous()
+        a, bt = alphas.float(), betas.float()
+        for i in progress():
+            for r in range(num_resamples):
+                j = int(r == num_resamples - 1)
+                ab = torch.stack([a[i], bt[i], a[i + j], bt[i + j]]).contiguous()
+                v = self.net(x, sigmas[i], **kwargs).float().contiguous()             # :340
+                ops.sampler_step(x, v, ab, x)                                         # :341-345
+                noise = torch.randn_like(source).float().expand_as(x).contiguous()    # :346
+                ops.inpaint_blend(x, src, noise, mask_u8, ab)                         # :346-350
+        return x.to(x_noisy.dtype)
+
+
 class VSampler(Sampler):
     """reference diffusion.py:158-190"""
 

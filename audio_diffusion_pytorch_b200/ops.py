@@ -318,6 +318,14 @@ def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:
     return x_next
 
 
+def inpaint_blend(x: Tensor, source: Tensor, noise: Tensor, mask_u8: Tensor, ab: Tensor) -> Tensor:
+    """In place: x = ab[2]*source + ab[3]*noise where mask (VInpainter, reference diffusion.py:346-350)."""
+    _launch(lambda: _lib.lib().adp_inpaint_blend(x.data_ptr(), source.data_ptr(), noise.data_ptr(),
+                                                 mask_u8.data_ptr(), ab.data_ptr(), x.numel(), _stream()),
+            "adp_inpaint_blend", lambda: ("inpaint_blend", 0, _nb(x, source, noise, mask_u8)))
+    return x
+
+
 # ----------------------------------------------------------------------------- backward
 def pack_conv_dgrad(w: Tensor) -> Tensor:
     """Weights of the data-gradient conv: dA[t] = sum_j dOut[t + o_j] @ Wt_j with the taps
@@ -326,18 +334,21 @@ def pack_conv_dgrad(w: Tensor) -> Tensor:
 
 
 def wgrad(g: Tensor, x: Tensor, dw: Tensor, *, n: int, k: int, off: int = 0, g_col0: int = 0,
-          x_col0: int = 0) -> Tensor:
-    """dw[n_, k_] += sum_{b,t} g[b,t,g_col0+n_] * x[b,t+off,x_col0+k_]; g, x bf16 [B,T,ld]."""
+          x_col0: int = 0, ntaps: int = 1) -> Tensor:
+    """dw[n_, k_] += sum_{b,t} g[b,t,g_col0+n_] * x[b,t+off,x_col0+k_]; g, x bf16 [B,T,ld].
+    ntaps=3: dw is [3, n, k] and tap j uses row offset off + j (a whole k=3 conv in one launch)."""
     a = WgradArgs()
+    a.ntaps = ntaps
+    a.tap_stride = dw.stride(0) if ntaps == 3 else 0
     a.g, a.x, a.dw = g.data_ptr(), x.data_ptr(), dw.data_ptr()
     a.B, a.T = g.shape[0], g.shape[1]
     a.n, a.k = n, k
-    a.ldg, a.ldx, a.ldw = g.stride(1), x.stride(1), dw.stride(0)
+    a.ldg, a.ldx, a.ldw = g.stride(1), x.stride(1), dw.stride(-2)
     a.g_cols, a.x_cols = g.shape[2], x.shape[2]
     a.g_col0, a.x_col0, a.off = g_col0, x_col0, off
     _launch(lambda: _lib.lib().adp_wgrad(C.byref(a), _stream()), "adp_wgrad",
-            lambda: (f"wgrad[M={g.shape[0] * g.shape[1]} n={n} k={k}]",
-                     2.0 * g.shape[0] * g.shape[1] * n * k, (g.shape[0] * g.shape[1]) * (n + k) * 2))
+            lambda: (f"wgrad[M={g.shape[0] * g.shape[1]} n={n} k={k}{' x3' if ntaps == 3 else ''}]",
+                     2.0 * g.shape[0] * g.shape[1] * n * k * ntaps, (g.shape[0] * g.shape[1]) * (n + k) * 2))
     return dw
 
 

@@ -155,8 +155,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
 
     def conv3_bwd(dy: Tensor, a_in: Tensor, gw: Tensor, da: Tensor, wd: Tensor, C: int):
         """dy: grad of the conv output; a_in: its input; writes da, accumulates dW (3 taps)."""
-        for tap, off in enumerate((-1, 0, 1)):
-            ops.wgrad(dy, a_in, gw[tap], n=C, k=C, off=off)
+        ops.wgrad(dy, a_in, gw, n=C, k=C, off=-1, ntaps=3)
         ops.conv_gemm(dy, wd, da, c_in=C, n_valid=C, taps=(-1, 0, 1))
 
     # ---- AttentionItem / CrossAttentionItem (a_unet): x + to_out(softmax(q k^T / 8) v)
@@ -456,8 +455,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             finals.append(lambda: grads.__setitem__(id(lv.up.weight), gw3.permute(1, 2, 0)))
 
             def up_wgrad():
-                for tap, off in enumerate((-1, 0, 1)):
-                    ops.wgrad(dys, x_last, gw3[tap], n=Co, k=C, off=off)
+                ops.wgrad(dys, x_last, gw3, n=Co, k=C, off=-1, ntaps=3)
 
             def up_dgrad():
                 ops.conv_gemm(dys, wd_up, dx_last, c_in=Co, n_valid=C, taps=(-1, 0, 1))
@@ -512,6 +510,27 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
     plan.backward_program = backward_program
     plan.P, plan.n_dss = P, dss_all.numel()
     return plan
+
+
+@torch.no_grad()
+def _refresh_dgrad_packs(plan: _TrainPlan, net: B200UNet) -> None:
+    """Transposed / tap-reversed weight packs of the data-gradient GEMMs after a weight update:
+    captured into a CUDA graph on first use (same reasoning as B200UNet._repack)."""
+    if not net.use_cuda_graph:
+        for r in plan.refreshers:
+            r()
+        return
+    if getattr(plan, "refresh_graph", None) is None:
+        for r in plan.refreshers:
+            r()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for r in plan.refreshers:
+                r()
+        plan.refresh_graph = g
+    else:
+        plan.refresh_graph.replay()
 
 
 def _run(plan: _TrainPlan, which: str, use_graph: bool) -> None:
@@ -625,9 +644,7 @@ class _UNetFn(torch.autograd.Function):
             ops.device_check()
             plan = net._plans[key] = build_train_plan(net, B, T, M, mode, want_dxin)
         elif plan.version != net._version():
-            with torch.no_grad():
-                for r in plan.refreshers:
-                    r()
+            _refresh_dgrad_packs(plan, net)
             plan.version = net._version()
         plan.x.copy_(x)
         if net.append_channels:

@@ -230,6 +230,7 @@ class B200UNet(nn.Module):
         self._packed_version = None
         self._fingerprint = None
         self._storage_sig = None
+        self._repack_graph = None
         self.use_cuda_graph = True
         # GroupNorm+SiLU applied inside the conv GEMM by transform warps (adp_conv_gemm gn_*).
         # Verified bit-compatible with the two-kernel path but measured SLOWER on the README
@@ -274,6 +275,7 @@ class B200UNet(nn.Module):
         self._packed = None
         self._packed_version = None
         self._fingerprint = None
+        self._repack_graph = None
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -313,11 +315,30 @@ class B200UNet(nn.Module):
         if self._packed is not None:
             # weights changed (optimizer step): refresh the SAME tensors in place, so captured
             # CUDA graphs and plans that hold their addresses stay valid
-            _copy_tree(self._packed, self._compute_packed())
+            self._repack()
             self._packed_version = v
             return self._packed
         self._packed, self._packed_version = self._compute_packed(), v
         return self._packed
+
+    @torch.no_grad()
+    def _repack(self) -> None:
+        """In-place refresh of every packed weight.  The re-layout is ~500 small permute / cast /
+        fold launches whose HOST cost (12 ms per training step, profiles/r2_train_profile_start.txt)
+        dwarfed their device time: sources (the parameters) and destinations (the packs) have
+        fixed addresses, so the whole sequence is captured once into a CUDA graph and replayed."""
+        if not (self.use_cuda_graph and self.net.down.weight.is_cuda):
+            _copy_tree(self._packed, self._compute_packed())
+            return
+        if self._repack_graph is None:
+            _copy_tree(self._packed, self._compute_packed())       # eager once: allocator warm
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                _copy_tree(self._packed, self._compute_packed())
+            self._repack_graph = g
+        else:
+            self._repack_graph.replay()
 
     @torch.no_grad()
     def _compute_packed(self):
@@ -839,6 +860,52 @@ class B200UNet(nn.Module):
             plan.ss_all.copy_(table[i - first], non_blocking=True)
             self._execute(plan)
         return plan.x.clone().to(x_noisy.dtype)
+
+
+def _inpaint_loop(self, x_noisy: Tensor, source: Tensor, mask: Tensor, sigmas: Tensor, alphas: Tensor,
+                  betas: Tensor, num_resamples: int, progress=None, **kwargs) -> Tensor:
+    """VInpainter's loop (reference diffusion.py:338-352): per step `num_resamples` net evaluations;
+    each one advances x to the level of the NEXT step only on the last resample (otherwise it is
+    re-noised back to the current level), then the known region (mask) is replaced by the source
+    noised to that level.  One graph launch + one blend kernel per evaluation; the noise is drawn
+    with torch.randn_like(source) in the reference's order."""
+    assert x_noisy.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+    self._check_untracked_updates()
+    embedding = kwargs.get("embedding")
+    scale = kwargs.get("embedding_scale", 1.0)
+    B, T, Bh, M = self._shape_key(x_noisy, embedding, scale)
+    plan = self._plan(B, T, Bh, M, "sample", (float(scale) if Bh != B else None,
+                                              exists(kwargs.get("features"))))
+    self._stage_inputs(plan, x_noisy.float(), sigmas[0], kwargs.get("features"), embedding, scale,
+                       kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"))
+    for fn in plan.pre:
+        fn()
+    num_steps = sigmas.shape[0] - 1
+    a, b = alphas.float(), betas.float()
+    # ab[i][j]: coefficients of a step from level i to level i + j (j = 0: stay, re-noise)
+    ab = torch.stack([torch.stack([a[:-1], b[:-1], a[:-1], b[:-1]], 1),
+                      torch.stack([a[:-1], b[:-1], a[1:], b[1:]], 1)], 1).contiguous()
+    sig = sigmas.float().repeat(1, Bh // B).contiguous()
+    src = source.float().expand_as(plan.x).contiguous()
+    mask_u8 = mask.expand_as(plan.x).to(torch.uint8).contiguous()
+    block = max(1, self.cond_table_rows // Bh)
+    table, first = None, 0
+    for i in (range(num_steps) if progress is None else progress):
+        if table is None or not (first <= i < first + table.shape[0]):
+            first = (i // block) * block
+            n = min(block, num_steps - first)
+            feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
+            table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
+        plan.ss_all.copy_(table[i - first], non_blocking=True)
+        for r in range(num_resamples):
+            plan.ab.copy_(ab[i, int(r == num_resamples - 1)], non_blocking=True)
+            self._execute(plan)
+            ops.inpaint_blend(plan.x, src, torch.randn_like(source).float().expand_as(plan.x).contiguous(),
+                              mask_u8, plan.ab)
+    return plan.x.clone().to(x_noisy.dtype)
+
+
+B200UNet.inpaint_loop = torch.no_grad()(_inpaint_loop)
 
 
 def _copy_tree(dst, src) -> None:

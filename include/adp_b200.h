@@ -220,6 +220,13 @@ int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t stream);
 int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_next, int64_t n,
                      adp_stream_t stream);
 
+/* VInpainter blend (reference diffusion.py:346-350): where mask != 0,
+ * x = ab[2]*source + ab[3]*noise  (the known region re-noised to the level the sampler step just
+ * produced; ab as in adp_stem_out / adp_sampler_step); elsewhere x is left as the sampler wrote it.
+ * x, source, noise fp32 [n]; mask uint8 [n]. */
+int adp_inpaint_blend(float* x, const float* source, const float* noise, const uint8_t* mask,
+                      const float* ab, int64_t n, adp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Backward (training) entry points: VDiffusion loss.backward() through UNetV0
  * (reference diffusion.py:82-95 + autograd over the a_unet blocks).  Data gradients are
@@ -239,6 +246,9 @@ typedef struct adp_wgrad_args {
   int32_t ldg, ldx, ldw;
   int32_t g_cols, x_cols; /* valid columns of g / x rows (TMA extents)    */
   int32_t g_col0, x_col0, off;
+  int32_t ntaps;      /* 0/1: one tap at row offset `off`; 3: the taps off, off+1, off+2 of a k=3
+                         conv in one launch, tap j written to dw + j*tap_stride                 */
+  int64_t tap_stride; /* floats between the dW slabs of consecutive taps (ntaps == 3)           */
 } adp_wgrad_args;
 int adp_wgrad(const adp_wgrad_args* args, adp_stream_t stream);
 

@@ -117,11 +117,34 @@ def case_cfg3_readme_scale():
                         param_fingerprint=fingerprint(m_port), seed=22, length=T)
 
 
+def case_tiny_inpaint():
+    """VInpainter (diffusion.py:306-354): port == reference with the same RNG stream; golden run
+    with a pre-drawn noise sequence so that a CUDA implementation can be fed the same draws."""
+    m_ref, m_port = build(TINY)
+    g = torch.Generator().manual_seed(23)
+    source = torch.randn(2, 2, 4096, generator=g)
+    mask = torch.zeros(2, 2, 4096, dtype=torch.bool)
+    mask[..., :1500] = True
+    mask[1, :, 3000:3600] = True
+    steps, resamples = 4, 2
+    torch.manual_seed(5)
+    s_ref = ref.VInpainter(net=m_ref.net)(source, mask, num_steps=steps, num_resamples=resamples)
+    torch.manual_seed(5)
+    s_port = port.VInpainterPort(net=m_port.net)(source, mask, num_steps=steps, num_resamples=resamples)
+    same(s_port, s_ref, "VInpainter 4 steps x 2 resamples")
+    # the draws the run consumed are reproducible: torch.manual_seed(5), then randn_like(source)
+    # once for x_noisy and once per (step, resample), on the CPU generator
+    np.savez_compressed(os.path.join(OUT, "tiny_inpaint.npz"), source_seed=23, rng_seed=5,
+                        mask_spans=np.array([[0, 0, 1500], [1, 0, 1500], [1, 3000, 3600]]),
+                        out=s_ref.numpy(), num_steps=steps, num_resamples=resamples,
+                        param_fingerprint=fingerprint(m_port))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for case in (case_tiny_50_steps, case_cfg3_readme_scale, case_readme_full_size):
+    for case in (case_tiny_50_steps, case_tiny_inpaint, case_cfg3_readme_scale, case_readme_full_size):
         if only and case.__name__ not in only:
             continue
         print(case.__name__)

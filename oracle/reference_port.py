@@ -195,6 +195,33 @@ class VSamplerPort(nn.Module):
         return x_noisy
 
 
+class VInpainterPort(nn.Module):
+    """diffusion.py:306-354 (VInpainter) with LinearSchedule."""
+
+    def __init__(self, net: nn.Module, start: float = 1.0, end: float = 0.0):
+        super().__init__()
+        self.net, self.start, self.end = net, start, end
+
+    @torch.no_grad()
+    def forward(self, source: Tensor, mask: Tensor, num_steps: int, num_resamples: int,
+                show_progress: bool = False, x_noisy: Optional[Tensor] = None, **kwargs) -> Tensor:
+        x_noisy = torch.randn_like(source) if x_noisy is None else x_noisy           # :331
+        b = x_noisy.shape[0]
+        sigmas = torch.linspace(self.start, self.end, num_steps + 1, device=x_noisy.device)
+        sigmas = sigmas[:, None].expand(-1, b)                                        # :334
+        alphas, betas = half_circle(right_pad_dims(sigmas, x_noisy.ndim + 1))         # :335-336
+        for i in range(num_steps):                                                    # :339
+            for r in range(num_resamples):                                            # :340
+                v = self.net(x_noisy, sigmas[i], **kwargs)                            # :341
+                x_pred = alphas[i] * x_noisy - betas[i] * v                           # :342
+                n_pred = betas[i] * x_noisy + alphas[i] * v                           # :343
+                j = r == num_resamples - 1                                            # :345
+                x_noisy = alphas[i + j] * x_pred + betas[i + j] * n_pred              # :346
+                s_noisy = alphas[i + j] * source + betas[i + j] * torch.randn_like(source)
+                x_noisy = s_noisy * mask + x_noisy * ~mask                            # :350
+        return x_noisy
+
+
 # ---------------------------------------------------------------------------- models.py
 class DiffusionModelPort(nn.Module):
     """models.py:22-45 (DiffusionModel): one net shared by diffusion and sampler."""

@@ -319,3 +319,17 @@ def test_stem_input_gradient(ops, adapter):
     down = F.conv1d(xin, w_dn, b_dn, stride=f)                      # [B, c0, T/f]
     ((skip * dv).sum() + (down * dout.float().transpose(1, 2)).sum()).backward()
     close(dxin, xin.grad, 1e-4, 1e-4, "dxin")
+
+
+@pytest.mark.parametrize("B,T,n,k", [(2, 256, 64, 64), (2, 300, 128, 128), (1, 100, 32, 32), (4, 256, 1024, 1024),
+                                     (3, 1000, 256, 512), (2, 4096, 8, 32), (1, 64, 512, 96)])
+def test_wgrad_three_taps_fused(ops, B, T, n, k):
+    """The three taps of a k=3 convolution in one launch (row-shifted views of one X box)."""
+    g = bf(rnd(B, T, n, seed=11))
+    x = bf(rnd(B, T, k, seed=12))
+    dw = torch.zeros(3, n, k, device=DEV)
+    ops.wgrad(g, x, dw, n=n, k=k, off=-1, ntaps=3)
+    xp = F.pad(x.float(), (0, 0, 1, 1))                      # zero rows at t = -1 and t = T
+    for tap in range(3):
+        ref = torch.einsum("btn,btk->nk", g.float(), xp[:, tap:tap + T])
+        close(dw[tap], ref, 1e-2, 1e-3, f"fused wgrad tap {tap} B{B} T{T} n{n} k{k}")

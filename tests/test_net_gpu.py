@@ -284,3 +284,30 @@ def test_cfg3_readme_scale_vs_golden(adp, oracle_port, golden_dir):
     e = rel_l2(s, torch.from_numpy(g["sample3"]))
     print(f"cfg3 README scale, CFG sampler 3 steps: rel-L2 {e:.3e}")
     assert e <= 5e-3
+
+
+def test_vinpainter_vs_golden(adp, oracle_port, golden_dir, monkeypatch):
+    """VInpainter (reference diffusion.py:306-354): the known region keeps the source, the rest is
+    generated; 4 steps x 2 resamples against the unmodified reference.  torch.randn_like is fed the
+    draws the reference run consumed (CUDA and CPU generators produce different streams)."""
+    g = load(golden_dir, "tiny_inpaint.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**TINY)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    source = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["source_seed"])))
+    mask = torch.zeros(2, 2, 4096, dtype=torch.bool)
+    for b_, lo, hi in g["mask_spans"]:
+        mask[b_, :, lo:hi] = True
+    steps, resamples = int(g["num_steps"]), int(g["num_resamples"])
+    torch.manual_seed(int(g["rng_seed"]))                 # the reference run's CPU draws, in order
+    draws = iter([torch.randn(2, 2, 4096) for _ in range(1 + steps * resamples)])
+    monkeypatch.setattr(torch, "randn_like", lambda t_, **kw: next(draws).to(t_))
+    inpainter = adp.VInpainter(net=model.net)
+    out = inpainter(source.to(DEV), mask.to(DEV), num_steps=steps, num_resamples=resamples)
+    e = rel_l2(out, torch.from_numpy(g["out"]))
+    print(f"VInpainter 4 steps x 2 resamples: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    # the last step ends at sigma = 0: alpha = 1, beta = 0 -> the known region IS the source
+    assert rel_l2(out.cpu()[mask], source[mask]) <= 1e-5

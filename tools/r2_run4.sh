@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+bash tools/gpu_tests_files.sh tests/test_bwd_ops_gpu.py tests/test_train_gpu.py > gpurun_out/tests_digest.txt 2>&1
+grep -E "^==|FAILED|Error|timed out" gpurun_out/tests_digest.txt | head -30
+python tools/time_train.py > gpurun_out/train_profile2.txt 2>&1; grep -v Warn gpurun_out/train_profile2.txt | head -64
