@@ -37,26 +37,39 @@ template <int C>
 struct MidCfg {
   static constexpr int TB = C == 32 ? 256 : 128;       // rows per tile
   static constexpr int TPR = 256 / TB;                 // staging threads per row
-  static constexpr int RS = C * 2 + 16;                // padded smem row stride (bytes)
+  static constexpr int RS = C * 2 + 16;                // padded smem row stride of s_x (bytes)
   static constexpr int WS = 3 * C * 2 + 16;            // padded stride of one W row (n) in smem
   static constexpr int MB = TB / 8 / 16;               // m16 blocks per warp
   static constexpr int NT = C / 8;                     // n8 tiles
+  static constexpr int OS = C + 4;                     // padded fp32 row stride of s_o (floats)
+  static constexpr int LPR = C / 8;                    // epilogue lanes per row (8 channels each)
+  static constexpr int ER = TB * LPR / 256;            // epilogue rows per thread
   static constexpr int X_BYTES = (TB + 2) * RS;
-  static constexpr int R_BYTES = TB * RS;
+  static constexpr int O_BYTES = TB * OS * 4;
   static constexpr int W_BYTES = C * WS;
-  static constexpr int SMEM = 2 * X_BYTES + 2 * R_BYTES + W_BYTES;
+  static constexpr int SMEM = X_BYTES + O_BYTES + W_BYTES;
 };
 
+// Per tile: (1) the prefetched rows are activated (GroupNorm + SiLU) into s_x; (2) the next
+// tile's rows and this tile's residual rows are requested; (3) conv3 as an mma.sync GEMM over
+// overlapping row windows of s_x; (4) the fp32 accumulators go to s_o in row-major order and
+// (5) the row-wise epilogue (bias is already in the accumulator; + residual, LayerNorm + FiLM,
+// statistics) runs with ONE thread per 8 consecutive channels of a row: 16-byte residual loads
+// and output stores, FiLM coefficients of the thread's 8 channels in registers, 3 shuffles per
+// reduction.  (The first version ran the epilogue in the accumulator-fragment layout: 4-byte
+// stores, 4-byte shared-memory residual reads and a shuffle chain per fragment row made the
+// kernel issue/latency bound at 15-40 % of HBM bandwidth, profiles/r2_ncu_mid_conv64.txt.)
 template <int C>
 __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_args a) {
   using Cfg = MidCfg<C>;
   constexpr int TB = Cfg::TB, TPR = Cfg::TPR, RS = Cfg::RS, WS = Cfg::WS, MB = Cfg::MB, NT = Cfg::NT;
+  constexpr int OS = Cfg::OS, LPR = Cfg::LPR, ER = Cfg::ER;
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* s_x = smem;                               // [2][TB+2][RS]  activated rows t0-1 .. t0+TB
-  uint8_t* s_r = smem + 2 * Cfg::X_BYTES;            // [2][TB][RS]    residual rows
-  uint8_t* s_w = s_r + 2 * Cfg::R_BYTES;             // [C][WS]        W[n][k = tap*C + ci] bf16
+  uint8_t* s_x = smem;                                          // [TB+2][RS] activated rows t0-1 .. t0+TB
+  float* s_o = reinterpret_cast<float*>(smem + Cfg::X_BYTES);   // [TB][OS]   conv output (fp32)
+  uint8_t* s_w = smem + Cfg::X_BYTES + Cfg::O_BYTES;            // [C][WS]    W[n][k = tap*C + ci] bf16
   __shared__ __align__(16) float s_ga[C], s_de[C];   // GroupNorm a, d per channel
   __shared__ __align__(16) float s_sc[C], s_sh[C];   // FiLM 1+scale, shift
   __shared__ float s_bias[C];
@@ -110,25 +123,24 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
 
   // staging: thread -> (row, 32-channel part); 4 x 16 bytes each
   const int srow = tid / TPR, spart = tid % TPR;
+  // epilogue: thread -> 8 channels [8*el, 8*el+8) of rows erow0 + i*(256/LPR)
+  const int el = tid % LPR, erow0 = tid / LPR;
+  float fsc[8], fsh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fsc[j] = s_sc[el * 8 + j]; fsh[j] = s_sh[el * 8 + j]; }
 
-  auto load_tile = [&](int tile, uint4 (&xr)[4], uint4 (&hr)[4], uint4 (&rr)[4]) {
+  auto load_tile = [&](int tile, uint4 (&xr)[4], uint4 (&hr)[4]) {
     const int t0 = tile * TB;
     const int t = t0 + srow;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       xr[i] = make_uint4(0, 0, 0, 0);
-      rr[i] = make_uint4(0, 0, 0, 0);
       hr[i] = make_uint4(0, 0, 0, 0);
     }
     if (t < a.T) {
       const uint4* p = reinterpret_cast<const uint4*>(xb + static_cast<size_t>(t) * C + spart * 32);
 #pragma unroll
       for (int i = 0; i < 4; ++i) xr[i] = __ldg(p + i);
-      if (has_res) {
-        const uint4* pr = reinterpret_cast<const uint4*>(rb + static_cast<size_t>(t) * C + spart * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rr[i] = __ldg(pr + i);
-      }
     }
     if (tid < 2 * TPR) {        // halo rows t0-1 (first TPR threads) and t0+TB (next TPR)
       const int th = tid < TPR ? t0 - 1 : t0 + TB;
@@ -155,40 +167,44 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
     return o;
   };
 
-  float st_s[NT], st_q[NT];          // statistics of channels (8j + 2q, 8j + 2q + 1), summed
-#pragma unroll
-  for (int j = 0; j < NT; ++j) { st_s[j] = 0.f; st_q[j] = 0.f; }
+  // statistics of the thread's 8 channels: two halves of 4 (a half never straddles a group)
+  float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
 
   int tile = blockIdx.x;
-  uint4 xr[4], hr[4], rr[4];
-  if (tile < n_tiles) load_tile(tile, xr, hr, rr);
-  int buf = 0;
+  uint4 xr[4], hr[4];
+  if (tile < n_tiles) load_tile(tile, xr, hr);
   const uint32_t w_base = smem_u32(s_w);
-  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+  const uint32_t x_base = smem_u32(s_x);
+  for (; tile < n_tiles; tile += gridDim.x) {
     const int t0 = tile * TB;
-    uint8_t* xs = s_x + buf * Cfg::X_BYTES;
-    uint8_t* rs = s_r + buf * Cfg::R_BYTES;
     {
       const bool valid = t0 + srow < a.T;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<uint4*>(xs + (srow + 1) * RS + spart * 64 + i * 16) = activate(xr[i], i * 8, valid);
-        if (has_res) *reinterpret_cast<uint4*>(rs + srow * RS + spart * 64 + i * 16) = rr[i];
-      }
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(s_x + (srow + 1) * RS + spart * 64 + i * 16) = activate(xr[i], i * 8, valid);
       if (tid < 2 * TPR) {
         const int th = tid < TPR ? t0 - 1 : t0 + TB;
         const bool hv = th >= 0 && th < a.T;
-        uint8_t* dst = xs + (tid < TPR ? 0 : TB + 1) * RS + (tid % TPR) * 64;
+        uint8_t* dst = s_x + (tid < TPR ? 0 : TB + 1) * RS + (tid % TPR) * 64;
         // the halo thread's part is (tid % TPR), whose coefficients this thread holds only if it
         // equals spart: true by construction (tid % TPR == spart)
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + i * 16) = activate(hr[i], i * 8, hv);
       }
     }
-    if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, xr, hr, rr);   // prefetch
-    __syncthreads();
+    if (tile + gridDim.x < n_tiles) load_tile(tile + gridDim.x, xr, hr);   // prefetch
+    // residual rows of this tile in the epilogue's mapping, in flight during the MMAs
+    uint4 res[ER];
+    if (has_res) {
+#pragma unroll
+      for (int i = 0; i < ER; ++i) {
+        const int t = t0 + erow0 + i * (256 / LPR);
+        res[i] = make_uint4(0, 0, 0, 0);
+        if (t < a.T) res[i] = __ldg(reinterpret_cast<const uint4*>(rb + static_cast<size_t>(t) * C + el * 8));
+      }
+    }
+    __syncthreads();        // s_x complete; every thread has left the previous tile's epilogue (s_o)
 
-    const uint32_t x_base = smem_u32(xs);
     float acc[MB][NT][4];
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb)
@@ -223,75 +239,74 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
         }
       }
     }
-
-    // epilogue in accumulator layout: lane (g, q) owns rows g / g+8, channels 8j+2q, 8j+2q+1
+    // accumulator fragments -> row-major fp32 tile: lane (g, q) owns rows g / g+8, channels 8j+2q, +1
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
+      const int r = warp * (TB / 8) + mb * 16 + g;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int rl = warp * (TB / 8) + mb * 16 + g + h * 8;      // tile-local row
-        const int t = t0 + rl;
-        const bool ok = t < a.T;
-        float y0[NT], y1[NT];
+      for (int j = 0; j < NT; ++j) {
+        *reinterpret_cast<float2*>(s_o + r * OS + 8 * j + 2 * q) = make_float2(acc[mb][j][0], acc[mb][j][1]);
+        *reinterpret_cast<float2*>(s_o + (r + 8) * OS + 8 * j + 2 * q) = make_float2(acc[mb][j][2], acc[mb][j][3]);
+      }
+    }
+    __syncthreads();        // s_o complete (and every warp is done reading s_x)
+
+    // row-wise epilogue: this thread's 8 channels of ER rows
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          y0[j] = acc[mb][j][2 * h];
-          y1[j] = acc[mb][j][2 * h + 1];
-          if (has_res) {
-            const float2 r2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(rs + rl * RS + (8 * j + 2 * q) * 2));
-            y0[j] += r2.x; y1[j] += r2.y;
-          }
-        }
-        if (has_film) {   // following ModulationItem: LayerNorm over C (no affine) + FiLM
-          float m = 0.f;
+    for (int i = 0; i < ER; ++i) {
+      const int rl = erow0 + i * (256 / LPR);
+      const int t = t0 + rl;
+      const float4 o0 = *reinterpret_cast<const float4*>(s_o + rl * OS + el * 8);
+      const float4 o1 = *reinterpret_cast<const float4*>(s_o + rl * OS + el * 8 + 4);
+      float y[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      if (has_res) {
+        const float2 r0 = unpack_bf16(res[i].x), r1 = unpack_bf16(res[i].y);
+        const float2 r2 = unpack_bf16(res[i].z), r3 = unpack_bf16(res[i].w);
+        y[0] += r0.x; y[1] += r0.y; y[2] += r1.x; y[3] += r1.y;
+        y[4] += r2.x; y[5] += r2.y; y[6] += r3.x; y[7] += r3.y;
+      }
+      if (has_film) {   // following ModulationItem: LayerNorm over C (no affine) + FiLM
+        float m = ((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]));
 #pragma unroll
-          for (int j = 0; j < NT; ++j) m += y0[j] + y1[j];
-          m += __shfl_xor_sync(0xffffffffu, m, 1);
-          m += __shfl_xor_sync(0xffffffffu, m, 2);
-          m *= (1.f / C);
-          float v = 0.f;
+        for (int o = LPR >> 1; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+        m *= (1.f / C);
+        float v = 0.f;
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            y0[j] -= m; y1[j] -= m;
-            v += y0[j] * y0[j] + y1[j] * y1[j];
-          }
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          const float rstd = rsqrtf(v * (1.f / C) + a.ln_eps);
+        for (int j = 0; j < 8; ++j) { y[j] -= m; v += y[j] * y[j]; }
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            const float2 sc = *reinterpret_cast<const float2*>(&s_sc[8 * j + 2 * q]);
-            const float2 sh = *reinterpret_cast<const float2*>(&s_sh[8 * j + 2 * q]);
-            y0[j] = y0[j] * rstd * sc.x + sh.x;
-            y1[j] = y1[j] * rstd * sc.y + sh.y;
-          }
-        }
-        if (ok) {
+        for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = rsqrtf(v * (1.f / C) + a.ln_eps);
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-            const uint32_t o = pack_bf16(y0[j], y1[j]);
-            *reinterpret_cast<uint32_t*>(yb + static_cast<size_t>(t) * C + 8 * j + 2 * q) = o;
-            const float2 r = unpack_bf16(o);          // statistics of the ROUNDED values
-            st_s[j] += r.x + r.y;
-            st_q[j] += r.x * r.x + r.y * r.y;
-          }
-        }
+        for (int j = 0; j < 8; ++j) y[j] = y[j] * rstd * fsc[j] + fsh[j];
+      }
+      uint4 ov;
+      ov.x = pack_bf16(y[0], y[1]); ov.y = pack_bf16(y[2], y[3]);
+      ov.z = pack_bf16(y[4], y[5]); ov.w = pack_bf16(y[6], y[7]);
+      if (t < a.T) {
+        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(t) * C + el * 8) = ov;
+        const float2 q0 = unpack_bf16(ov.x), q1 = unpack_bf16(ov.y);   // statistics of the ROUNDED values
+        const float2 q2 = unpack_bf16(ov.z), q3 = unpack_bf16(ov.w);
+        st_s[0] += (q0.x + q0.y) + (q1.x + q1.y);
+        st_q[0] += (q0.x * q0.x + q0.y * q0.y) + (q1.x * q1.x + q1.y * q1.y);
+        st_s[1] += (q2.x + q2.y) + (q3.x + q3.y);
+        st_q[1] += (q2.x * q2.x + q2.y * q2.y) + (q3.x * q3.x + q3.y * q3.y);
       }
     }
   }
   if (a.stats_out) {
     const int gsz = C / a.groups;
+    // lanes el, el+LPR, ... of a warp hold the same channels: fold, then one atomic per (warp, half)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
+    for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {       // over the 8 rows (g) a warp instruction covers
-        st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], o);
-        st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], o);
+      for (int o = LPR; o < 32; o <<= 1) {
+        st_s[hf] += __shfl_xor_sync(0xffffffffu, st_s[hf], o);
+        st_q[hf] += __shfl_xor_sync(0xffffffffu, st_q[hf], o);
       }
-      if (lane < 4) {                          // lane == q; the channel pair lies in one group
-        const int gi = (8 * j + 2 * q) / gsz;
-        atomicAdd(&s_stats[2 * gi], st_s[j]);
-        atomicAdd(&s_stats[2 * gi + 1], st_q[j]);
+      if (lane < LPR) {
+        const int gi = (el * 8 + hf * 4) / gsz;
+        atomicAdd(&s_stats[2 * gi], st_s[hf]);
+        atomicAdd(&s_stats[2 * gi + 1], st_q[hf]);
       }
     }
     __syncthreads();

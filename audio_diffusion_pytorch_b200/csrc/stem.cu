@@ -555,7 +555,8 @@ extern "C" int adp_narrow_conv(const adp_narrow_conv_args* args, adp_stream_t st
             "adp_narrow_conv: C=%d is not built (8, 32, 64); wider levels use adp_conv_gemm", a.C);
   ADP_CHECK(a.groups > 0 && a.C % a.groups == 0 && a.groups <= 64, "adp_narrow_conv: groups=%d", a.groups);
   if (a.C != 8) {
-    ADP_CHECK((a.C / a.groups) % 2 == 0, "adp_narrow_conv: group size %d must be even", a.C / a.groups);
+    ADP_CHECK(!a.stats_out || (a.C / a.groups) % 4 == 0,
+              "adp_narrow_conv: group size %d must be a multiple of 4 (fused statistics)", a.C / a.groups);
     if (int e = mid_conv(a, as_stream(stream))) return e;
     ADP_LAUNCH_CHECK();
     return 0;

@@ -543,7 +543,7 @@ class B200UNet(nn.Module):
             narrow = C == 8
             # thin levels (C = 32, 64) are HBM-bound: one fused ConvBlock kernel (mid_conv.cu)
             # instead of gn_silu -> conv_gemm (-> ln_film)
-            thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 2 == 0)
+            thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 4 == 0)
             for idx, ip in enumerate(items_p):
                 ss = ss_all[:, ip["ss_off"]:]
                 has_att, has_cross = "att" in ip, "cross" in ip

@@ -392,45 +392,65 @@ def main():
     value = clips * CLIP_SECONDS / (ms_per_step * 1e-3)
     e2e_value = clips * CLIP_SECONDS / (e2e_ms / args.steps * 1e-3)
 
-    # ---- roofline of the dominant kernel: instrumented eager pass of the same plan
+    # ---- roofline of the dominant kernel/shape of one net evaluation.
+    # (1) in-graph durations per kernel + shape: the step's CUDA graph re-captured with programmatic
+    #     dependent launch OFF (with PDL a kernel's duration includes the time it waits for its
+    #     predecessor) and replayed under CUPTI activity tracing, AFTER the timed region;
+    # (2) the same launches timed with CUDA events in an eager pass of the plan (upper bound:
+    #     includes host launch gaps).  `achieved` uses (1); (2) is reported next to it.
+    from audio_diffusion_pytorch_b200 import _lib
     plan = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
     cond_plan = next((p for k, p in net._plans.items() if k[0] == "cond"), None)
+    n_kernels, n_pre = plan.n_kernels, len(getattr(plan, "pre", []))
     table = net.profile_plan(plan, iters=5)
     hbm, tf_burst, tf_sust, which = peaks()
-    top = max(table.values(), key=lambda r: r["ms_total"])
-    step_ms = sum(r["ms_total"] for r in table.values())
-    ai = top["flops"] / max(top["bytes"], 1)
-    if ai >= tf_sust * 1e12 / (hbm * 1e9):
-        achieved = top["flops"] / (top["ms_avg"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s",
-                "frac": achieved / tf_sust}
-    else:
-        achieved = top["bytes"] / (top["ms_avg"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm}
-    traffic, traffic_src = ncu_traffic(top["name"])
-    roof.update({"kernel": top["name"], "launches_per_net_eval": top["count"],
-                 "share_of_step": top["ms_total"] / step_ms, "peak_source": which,
-                 "traffic": traffic, "traffic_source": traffic_src,
-                 "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"],
-                 "timing": "CUDA events around each launch of an eager pass of the captured plan "
-                           "(5 passes averaged); in-graph per-shape durations: profiles/r2_graph_profile.txt"})
-    # the same kernel/shape INSIDE the captured graph (CUPTI activity records of graph replays, run
-    # after the timed region; warm L2, no per-launch event gaps): the eager-event figure above is
-    # the conservative one, the truth for the real step lies between the two
+    gtab, busy_us, in_graph_err = None, None, None
     try:
         from tools.graph_profile import in_graph_table
-        gtab, _, busy_us, span_us = in_graph_table(
-            net, plan, lambda k: model.sample(dev_in, num_steps=k, **dev_kw, **kw), 4)
-        g = gtab.get(top["name"])
-        if g is not None:
-            roof["in_graph_us"] = g["us_avg"]
-            roof["achieved_in_graph"] = (top["flops"] / g["us_avg"] / 1e6 if roof["bound"] == "tensor"
-                                         else top["bytes"] / g["us_avg"] / 1e3)
-            roof["frac_in_graph"] = roof["achieved_in_graph"] / roof["peak"]
+        saved = dict(net._plans)
+        net._plans.clear()
+        _lib.lib().adp_debug_set(6, 0)
+        try:
+            for _ in range(2):
+                model.sample(dev_in, num_steps=2, **dev_kw, **kw)
+            plan_np = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
+            gtab, _, busy_us, _ = in_graph_table(
+                net, plan_np, lambda k: model.sample(dev_in, num_steps=k, **dev_kw, **kw), 4)
+        finally:
+            _lib.lib().adp_debug_set(6, 1)
+            net._plans.clear()
+            net._plans.update(saved)
+    except Exception as exc:                      # profiler unavailable: event-timed numbers only
+        in_graph_err = repr(exc)[:200]
+    if gtab:
+        top_name = max(gtab, key=lambda k: gtab[k]["us_total"])
+        top_us, top_share = gtab[top_name]["us_avg"], gtab[top_name]["us_total"] / busy_us
+        top = table.get(top_name) or {"name": top_name, "flops": gtab[top_name]["flops"],
+                                      "bytes": gtab[top_name]["bytes"], "count": gtab[top_name]["count"],
+                                      "ms_avg": float("nan"), "ms_total": float("nan")}
+    else:
+        top = max(table.values(), key=lambda r: r["ms_total"])
+        top_us = top["ms_avg"] * 1e3
+        top_share = top["ms_total"] / sum(r["ms_total"] for r in table.values())
+    ai = top["flops"] / max(top["bytes"], 1)
+    tensor_bound = ai >= tf_sust * 1e12 / (hbm * 1e9)
+    work, peak, unit = ((top["flops"] / 1e6, tf_sust, "TFLOP/s") if tensor_bound
+                        else (top["bytes"] / 1e3, hbm, "GB/s"))
+    achieved = work / top_us
+    roof = {"bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "kernel_us": top_us,
+            "timing": ("in-graph (CUDA graph of the step re-captured with PDL off, CUPTI activity records, "
+                       "4 steps averaged)" if gtab else "CUDA events around each launch of an eager pass"),
+            "achieved_eager_events": work / (top["ms_avg"] * 1e3), "eager_event_us": top["ms_avg"] * 1e3}
+    if in_graph_err:
+        roof["in_graph_error"] = in_graph_err
+    if busy_us is not None:
         roof["kernel_busy_us_per_net_eval"] = busy_us
-    except Exception as exc:                      # profiler unavailable: keep the event-timed number
-        roof["in_graph_error"] = repr(exc)[:200]
+    traffic, traffic_src = ncu_traffic(top["name"])
+    roof.update({"kernel": top["name"], "launches_per_net_eval": top["count"],
+                 "share_of_step": top_share, "peak_source": which,
+                 "traffic": traffic, "traffic_source": traffic_src,
+                 "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"]})
     # whole-step roofline: sum over levels of max(flop time, byte time)
     t_bound = sum(max(r["flops"] / (tf_sust * 1e12), r["bytes"] / (hbm * 1e9)) * r["count"]
                   for r in table.values())
@@ -443,7 +463,6 @@ def main():
                   f"{r['bytes'] / max(r['ms_avg'], 1e-9) / 1e6:8.1f} GB/s", file=sys.stderr)
 
     h2d = host_in.numel() * 4 + sum(v.numel() * 4 for v in host_kw.values())
-    n_pre = len(getattr(plan, "pre", []))
     line = {"metric": w["metric"], "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -453,11 +472,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": host_out.numel() * 4},
             # per step the net's kernels; per sample() call the conditioning (+ context K/V) launches
-            "gpu_launches": (plan.n_kernels * num_steps + (6 if cond_plan is not None else 0) + n_pre) * args.steps,
+            "gpu_launches": (n_kernels * num_steps + (6 if cond_plan is not None else 0) + n_pre) * args.steps,
             "ms_per_net_eval": ms_per_step / num_steps,
             "roofline": roof}
     if not args.no_train and args.config == "cfg2":
         del model, net, plan
+        gtab = table = None
         torch.cuda.empty_cache()
         line["train_step"] = train_step_bench(adp, dev, world, dist, steps=5, warmup=3)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
