@@ -35,7 +35,12 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
   // memory with ONE atomic per parameter per block (one block per tile meant 4096 same-address
   // atomics per parameter and a 130 us kernel, profiles/r2_train_profile_start.txt)
   const int n_tiles = (a.T + kTB - 1) / kTB;
-  float acc_w = 0.f;                                   // this thread's dw / dbias element
+  static_assert(C == 8, "register layout of the weight-gradient accumulators assumes C = 8");
+  float gwr[2][C][3], gb[2] = {0.f, 0.f};              // dw[2 co][C ci][3 taps], dbias[2 co]
+#pragma unroll
+  for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) { gwr[c2][ci][0] = 0.f; gwr[c2][ci][1] = 0.f; gwr[c2][ci][2] = 0.f; }
   for (int i = threadIdx.x; i < 3 * C * C; i += kTB) {
     const int k = i / (C * C), r = i - k * C * C, co = r / C, ci = r - co * C;
     s_w[i] = a.w[(co * C + ci) * 3 + k];
@@ -130,21 +135,62 @@ narrow_conv_bwd_kernel(const adp_narrow_conv_bwd_args a) {
     }
   }
   // (2) weight gradient: thread j < 3*C*C owns dw[co][ci][k]; threads after that own dbias[co]
+  // (2) weight gradient: thread = (position p of a 64-position pass, output-channel pair cg); its
+  // 2 x C x 3 dw elements and 2 dbias elements live in registers across all tiles of the block
   const int nvalid = min(kTB, a.T - t0);
-  if (threadIdx.x < 3 * C * C) {
-    const int co = threadIdx.x / (3 * C), r = threadIdx.x - co * 3 * C, ci = r / 3, k = r - ci * 3;
-    float acc = 0.f;
-    for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co] * s_a[(i + k) * C + ci];
-    acc_w += acc;
-  } else if (threadIdx.x < 3 * C * C + C) {
-    const int co = threadIdx.x - 3 * C * C;
-    float acc = 0.f;
-    for (int i = 0; i < nvalid; ++i) acc += s_dy[(i + 1) * C + co];
-    acc_w += acc;
+  {
+    const int cg = threadIdx.x & 3, p = threadIdx.x >> 2;
+#pragma unroll
+    for (int pass = 0; pass < kTB / 64; ++pass) {
+      const int i = pass * 64 + p;
+      if (i < nvalid) {
+        const float g0 = s_dy[(i + 1) * C + 2 * cg], g1 = s_dy[(i + 1) * C + 2 * cg + 1];
+        gb[0] += g0; gb[1] += g1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4* ar = reinterpret_cast<const float4*>(&s_a[(i + k) * C]);
+          const float4 a0 = ar[0], a1 = ar[1];
+          const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int ci = 0; ci < C; ++ci) { gwr[0][ci][k] += g0 * a8[ci]; gwr[1][ci][k] += g1 * a8[ci]; }
+        }
+      }
+    }
   }
   }  // tiles
-  if (threadIdx.x < 3 * C * C) atomicAdd(a.dw + threadIdx.x, acc_w);           // PyTorch layout [co][ci][k]
-  else if (threadIdx.x < 3 * C * C + C) atomicAdd(a.dbias + (threadIdx.x - 3 * C * C), acc_w);
+  {
+    // lanes with the same cg (stride 4) fold, then the 8 warps through smem: one atomic per element
+    __syncthreads();
+    float* s_part = s_a;                        // [8 warps][4 cg][50]; the tile buffers are dead
+    const int cg = threadIdx.x & 3, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto put = [&](int idx, float v) {
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) s_part[(warp * 4 + cg) * 50 + idx] = v;
+    };
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) put((c2 * C + ci) * 3 + k, gwr[c2][ci][k]);
+      put(48 + c2, gb[c2]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 * 50) {
+      const int cgo = threadIdx.x / 50, idx = threadIdx.x - cgo * 50;
+      float tot = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) tot += s_part[(w8 * 4 + cgo) * 50 + idx];
+      if (idx < 48) {                                    // (c2, ci, k) -> dw[co = 2*cgo + c2][ci][k]
+        const int c2 = idx / 24, r = idx - c2 * 24;
+        atomicAdd(a.dw + (2 * cgo + c2) * 3 * C + r, tot);
+      } else {
+        atomicAdd(a.dbias + 2 * cgo + (idx - 48), tot);
+      }
+    }
+  }
   __syncthreads();
   if (threadIdx.x < C) {
     atomicAdd(a.dgamma + threadIdx.x, s_red[threadIdx.x]);
@@ -186,6 +232,19 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
   float acc_it[kSoItems];
 #pragma unroll
   for (int k = 0; k < kSoItems; ++k) acc_it[k] = 0.f;
+  // fast path (the shapes of every model class: c0 = 8, <= 2 output and <= 4 input channels):
+  // one thread per POSITION with every parameter gradient in its own register, reduced across the
+  // block once at the very end -- the generic path below gives each parameter to one thread, which
+  // leaves 3/4 of the block idle in 256-step dot products (1.2 ms for this one kernel at B = 4)
+  const bool fast = a.c0 == 8 && a.co <= 2 && cin <= 4;
+  float fw[2][8][3], fb[2] = {0.f, 0.f}, fg[2] = {0.f, 0.f}, fad[2][4], fadb[2] = {0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { fw[o][c][0] = 0.f; fw[o][c][1] = 0.f; fw[o][c][2] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fad[o][c] = 0.f;
+  }
   const int n_tiles = (a.T + kTB - 1) / kTB;
   const int n_w = a.co * a.c0 * 3, n_ad = a.w_adapt ? a.co * cin : 0;
   const int n_items = n_w + a.co /*bias*/ + a.co /*gate*/ + n_ad + (a.w_adapt ? a.co : 0);
@@ -254,11 +313,50 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
       }
     }
   }
-  // (2) parameter gradients: flat work items, one dot product over the tile each
+  // (2) parameter gradients
+  if (fast) {
+    const int i = threadIdx.x;
+    if (i < nvalid) {
+      float dyv[2], dvv[2], yv[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const bool on = o < a.co;
+        dyv[o] = on ? s_dy[(i + 1) * a.co + o] : 0.f;
+        dvv[o] = on ? s_dv[i * a.co + o] : 0.f;
+        yv[o] = (on && a.bias) ? a.bias[o] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int u = t0 + i + k - 1;
+        if (u < 0 || u >= a.T) continue;
+        const float4* hr = reinterpret_cast<const float4*>(&s_h[(u / a.f - q0) * 8]);
+        const float4 h0 = hr[0], h1 = hr[1];
+        const float h8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          if (o >= a.co) break;
+          const float* wp = &s_w[(o * 3 + k) * 8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { fw[o][c][k] += dyv[o] * h8[c]; yv[o] += h8[c] * wp[c]; }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        fb[o] += dyv[o];
+        fg[o] += dvv[o] * yv[o];
+        if (a.w_adapt) {
+          fadb[o] += dvv[o];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < cin) fad[o][c] += dvv[o] * s_xin[i * cin + c];
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int kk = 0; kk < kSoItems; ++kk) {
     const int item = threadIdx.x + kk * kTB;
-    if (item >= n_items) break;
+    if (fast || item >= n_items) break;
     float acc = 0.f;
     if (item < n_w) {                         // dw[co][c0][k] (PyTorch layout)
       const int o = item / (a.c0 * 3), r = item - o * a.c0 * 3, c = r / 3, k = r - c * 3;
@@ -310,6 +408,50 @@ __global__ void __launch_bounds__(kTB) stem_out_bwd_kernel(const adp_stem_out_bw
     }
   }
   }  // tiles
+  if (fast) {
+    // block reduction of the per-position registers: warp sums -> smem [8 warps][62] -> one atomic
+    // per parameter; the item order is the generic path's (dw, dbias, dgate, dw_adapt, db_adapt)
+    __syncthreads();
+    float* s_red = s_dyn;                       // tile buffers are dead
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto put = [&](int idx, float v) {
+      v = warp_sum(v);
+      if (lane == 0) s_red[warp * 64 + idx] = v;
+    };
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) put((o * 8 + c) * 3 + k, fw[o][c][k]);       // 0..47
+      put(48 + o, fb[o]);
+      put(50 + o, fg[o]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) put(52 + o * 4 + c, fad[o][c]);
+      put(60 + o, fadb[o]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 62) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) tot += s_red[w8 * 64 + threadIdx.x];
+      const int idx = threadIdx.x;
+      if (idx < 48) {
+        const int o = idx / 24;
+        if (o < a.co) atomicAdd(a.dw + idx, tot);              // [co][8][3] flat: same index
+      } else if (idx < 50) {
+        if (idx - 48 < a.co) atomicAdd(a.dbias + (idx - 48), tot);
+      } else if (idx < 52) {
+        if (idx - 50 < a.co) atomicAdd(a.dgate + static_cast<size_t>(b) * a.ld_dgate + (idx - 50), tot);
+      } else if (idx < 60) {
+        const int o = (idx - 52) >> 2, c = (idx - 52) & 3;
+        if (a.w_adapt && o < a.co && c < cin) atomicAdd(a.dw_adapt + o * cin + c, tot);
+      } else {
+        if (a.w_adapt && idx - 60 < a.co) atomicAdd(a.db_adapt + (idx - 60), tot);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int kk = 0; kk < kSoItems; ++kk) {
     const int item = threadIdx.x + kk * kTB;

@@ -149,6 +149,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
             *reinterpret_cast<float4*>(drow + k0 + c0 + i) =
                 make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
                             __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        } else if (k0 + c0 + 32 <= p.k_valid && (p.ldw & 3) == 0 && (p.tap_stride & 3) == 0) {
+          // split-K over time: 16-byte vector reductions (one per 4 columns instead of four scalar
+          // atomics whose 32 lanes hit 32 different rows = 32 sectors per instruction)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(drow + k0 + c0 + i),
+                      make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -205,9 +213,14 @@ static int launch_wgrad(const adp_wgrad_args& a, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // split-K over time: every split ends in 128 x BN fp32 atomics, so keep >= 16 chunks per CTA
+  // split-K over time: every split ends in NT x 128 x BN fp32 reductions into dW.  Narrow outputs
+  // (few tiles) need many splits to fill the SMs; wide outputs pay for every split in atomics:
+  // cap the total reduction traffic at ~4 M elements and keep >= 4 chunks per CTA
   int splits = (2 * sms) / (n_tiles * k_tiles);
-  if (splits > p.total_chunks / 16) splits = p.total_chunks / 16;
+  const long out_elems = (long)NT * a.n * a.k;
+  const long by_atomics = (4L << 20) / (out_elems > 0 ? out_elems : 1);
+  if (splits > by_atomics) splits = (int)(by_atomics < 1 ? 1 : by_atomics);
+  if (splits > p.total_chunks / 4) splits = p.total_chunks / 4;
   if (splits < 1) splits = 1;
   p.chunks_per_split = (p.total_chunks + splits - 1) / splits;
   splits = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;

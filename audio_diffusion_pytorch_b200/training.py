@@ -117,6 +117,8 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
     flat = torch.zeros(int(1.25 * n_param) + 64 * (4 * n_param // 1000 + 4096), device=dev)
     cursor = [0]
 
+    specs: Dict[int, tuple] = {}           # id(param) -> (arena start, numel, view shape, permutation)
+
     def gbuf(shape):
         n = 1
         for d in shape:
@@ -124,11 +126,15 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         start = cursor[0]
         cursor[0] = start + (n + 63) // 64 * 64
         assert cursor[0] <= flat.numel(), "gradient arena too small"
+        gbuf.last = start
         return flat[start:start + n].view(*shape)
 
-    def grad_for(param, shape=None):
-        t = gbuf(tuple(param.shape) if shape is None else shape)
-        grads[id(param)] = t
+    def grad_for(param, shape=None, perm=None):
+        """Arena accumulator for `param`'s gradient: stored as `shape` (default: the parameter's),
+        handed to autograd as `.view(shape).permute(perm)` of a per-backward copy of the arena."""
+        shape = tuple(param.shape) if shape is None else tuple(shape)
+        t = gbuf(shape)
+        specs[id(param)] = (gbuf.last, t.numel(), shape, perm)
         return t
 
     n_tot = P["cond_n"]
@@ -292,7 +298,9 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                     a2, ip["w2"], rr, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
                 plan.fwd.append(modulation_fwd)
                 da = act(B, Tl, C)
-                gw = {"w1": gbuf((3, C, C)), "w2": gbuf((3, C, C))}
+                # [tap][co][ci] accumulators of the fused 3-tap wgrad -> PyTorch [co][ci][tap]
+                gw = {"w1": grad_for(r_.conv1.weight, (3, C, C), (1, 2, 0)),
+                      "w2": grad_for(r_.conv2.weight, (3, C, C), (1, 2, 0))}
 
                 def bwd(dy, x=x, h=h, rr=rr, a1=a1, a2=a2, ss=ss, dss=dss, xs=x_stats, hs=h_stats,
                         ip=ip, dr=dr, dh=dh, dx=dx, dxh=dxh, da=da, S1=S1, S2=S2, dgn1=dgn1,
@@ -306,9 +314,6 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                     ops.gn_silu_bwd(da, x, xs, ip["gn1"][0], ip["gn1"][1], dxh, dgn1[0], dgn1[1], S1, G)
                     ops.gn_bwd_apply(dxh, x, xs, S1, dx, G, dres=dr)
                     return dx
-                finals.append(lambda gw=gw, r_=r_: (
-                    grads.__setitem__(id(r_.conv1.weight), gw["w1"].permute(1, 2, 0)),
-                    grads.__setitem__(id(r_.conv2.weight), gw["w2"].permute(1, 2, 0))))
             grads[id(im.modulation.proj.weight)] = ("cond_w", ip["ss_off"], 2 * C)
             grads[id(im.modulation.proj.bias)] = ("cond_b", ip["ss_off"], 2 * C)
             chain = [bwd]
@@ -356,9 +361,8 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                                                   n_valid=C, bias=Lp["down_b"], stats=st0, groups=G))
             wd_down = packed_dgrad(lambda: ops.pack_linear(
                 lv.down.weight.detach().permute(0, 2, 1).reshape(C, kdim).t().contiguous()))
-            gw_down = gbuf((C, kdim))
-            finals.append(lambda: grads.__setitem__(
-                id(lv.down.weight), gw_down.view(C, lv.factor, lv.in_ch).permute(0, 2, 1)))
+            # [co][tap][ci] (the [B, T/f, f*C] view) -> PyTorch [co][ci][tap]
+            gw_down = grad_for(lv.down.weight, (C, lv.factor, lv.in_ch), (0, 2, 1)).view(C, kdim)
         x, st, items_down_bwd = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl)
         cur["down_end"] = cursor[0]
         inner = None
@@ -375,10 +379,9 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         x_last = x
         if i == 0:
             dw_up = grad_for(lv.up.weight)
-            dwa = grad_for(lv.adapter.weight, (lv.out_ch, lv.in_ch)) if lv.adapter is not None else None
+            dwa = (grad_for(lv.adapter.weight, (lv.out_ch, lv.in_ch, 1)).view(lv.out_ch, lv.in_ch)
+                   if lv.adapter is not None else None)
             dba = grad_for(lv.adapter.bias) if lv.adapter is not None else None
-            if lv.adapter is not None:
-                finals.append(lambda: grads.__setitem__(id(lv.adapter.weight), dwa.unsqueeze(-1)))
             dh0 = act(B, Tl, C)
             plan.fwd.append(lambda: ops.stem_out(
                 x_last, plan.x, Lp["up_w"], Lp["up_b"], gate, lv.factor, append=plan.append,
@@ -451,8 +454,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             plan.fwd.append(lambda: ops.conv_gemm(x_last, Lp["up_w"], y_up, c_in=C, n_valid=Co,
                                                   taps=(-1, 0, 1), bias=Lp["up_b"]))
             wd_up = packed_dgrad(lambda: ops.pack_conv_dgrad(lv.up.weight.detach()))
-            gw3 = gbuf((3, Co, C))
-            finals.append(lambda: grads.__setitem__(id(lv.up.weight), gw3.permute(1, 2, 0)))
+            gw3 = grad_for(lv.up.weight, (3, Co, C), (1, 2, 0))
 
             def up_wgrad():
                 ops.wgrad(dys, x_last, gw3, n=Co, k=C, off=-1, ntaps=3)
@@ -490,7 +492,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
     assert slot[0] <= arena.shape[0]
     plan.flat = flat
     plan.refreshers, plan.version = refreshers, net._version()
-    plan.grads, plan.finals = grads, finals
+    plan.grads, plan.finals, plan.specs = grads, finals, specs
     plan.ss_all, plan.dss_all = ss_all, dss_all
     # conditioning projection backward
     plan.dw_all = _zeros((n_tot, Fm), dev)
@@ -687,14 +689,25 @@ class _UNetFn(torch.autograd.Function):
             _run_backward_synced(plan, net, sync)
         for fin in plan.finals:
             fin()
+        # .grad must never alias the plan's arenas (they are rewritten by the next backward): ONE copy
+        # of the arena per backward, the gradients are views of that copy
+        fresh = plan.flat.clone()
+        cond_w, cond_b = plan.dw_all.clone(), plan.dbias_all.clone()
         out = []
         for p in ctx.params:
-            g = plan.grads.get(id(p))
-            if isinstance(g, tuple):
-                kind, off, n = g
-                g = plan.dw_all[off:off + n] if kind == "cond_w" else plan.dbias_all[off:off + n]
-            # clones: .grad must never alias the plan's arenas (they are rewritten next backward)
-            out.append(None if g is None else g.reshape(p.shape).to(p.dtype).clone())
+            spec = plan.specs.get(id(p))
+            if spec is not None:
+                start, n, shape, perm = spec
+                g = fresh[start:start + n].view(shape)
+                g = g.permute(perm) if perm is not None else g
+            else:
+                g = plan.grads.get(id(p))
+                if isinstance(g, tuple):
+                    kind, off, n = g
+                    g = cond_w[off:off + n] if kind == "cond_w" else cond_b[off:off + n]
+                elif g is not None:
+                    g = g.reshape(p.shape).clone()       # computed by a `final` (upsample conv folds)
+            out.append(None if g is None else (g if g.dtype == p.dtype else g.to(p.dtype)))
         dx = d_append = d_emb = None
         need = ctx.needs_input_grad        # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
         if plan.dxin is not None:
