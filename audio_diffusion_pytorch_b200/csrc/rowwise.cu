@@ -462,6 +462,32 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// Per-step inputs of the captured sampling step, selected ON THE DEVICE: the step graph is the same
+// for every step (and several steps can be captured back to back), the host only replays it.
+//   ctrl[0] = address of the conditioning table rows [n][ss_elems] (fp32), ctrl[1] = steps that
+//   share one table row (VInpainter resamples), step = iterations done since the host reset it
+__global__ void step_select_kernel(const int* __restrict__ step, const long long* __restrict__ ctrl,
+                                   const float* __restrict__ ab_table, float* __restrict__ ab_out,
+                                   float* __restrict__ ss_out, int64_t ss_elems) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int it = *step;
+  const float* table = reinterpret_cast<const float*>(ctrl[0]);
+  const long long div = ctrl[1] > 0 ? ctrl[1] : 1;
+  const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(it / div) * ss_elems);
+  float4* dst = reinterpret_cast<float4*>(ss_out);
+  const int64_t n4 = ss_elems >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+  if (blockIdx.x == 0 && threadIdx.x < 4) ab_out[threadIdx.x] = ab_table[static_cast<size_t>(it) * 4 + threadIdx.x];
+}
+__global__ void step_advance_kernel(int* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) *step += 1;
+}
+
 // VInpainter (reference diffusion.py:349-350): where mask, x := a1*source + b1*noise (the known
 // region re-noised to the level the sampler just stepped to); elsewhere x keeps the sampler's value
 __global__ void inpaint_blend_kernel(float* __restrict__ x, const float* __restrict__ source,
@@ -619,6 +645,24 @@ extern "C" int adp_silu_bf16(const float* x, void* y, int64_t n, adp_stream_t st
   ADP_CHECK(x && y && n > 0, "adp_silu_bf16: bad args");
   ADP_CUDA(launch_k(silu_bf16_kernel, dim3(pick_grid(static_cast<size_t>(n), 256, 148 * 4)),
                     dim3(256), (size_t)0, as_stream(stream), x, static_cast<__nv_bfloat16*>(y), n));
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_step_select(const int32_t* step, const int64_t* ctrl, const float* ab_table,
+                               float* ab_out, float* ss_out, int64_t ss_elems, adp_stream_t stream) {
+  ADP_CHECK(step && ctrl && ab_table && ab_out && ss_out && ss_elems > 0 && ss_elems % 4 == 0,
+            "adp_step_select: bad args");
+  ADP_CUDA(launch_k(step_select_kernel, dim3(pick_grid(static_cast<size_t>(ss_elems / 4), 256 * 4, 148 * 4)),
+                    dim3(256), (size_t)0, as_stream(stream), step, reinterpret_cast<const long long*>(ctrl),
+                    ab_table, ab_out, ss_out, ss_elems));
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_step_advance(int32_t* step, adp_stream_t stream) {
+  ADP_CHECK(step != nullptr, "adp_step_advance: null");
+  ADP_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(32), (size_t)0, as_stream(stream), step));
   ADP_LAUNCH_CHECK();
   return 0;
 }

@@ -144,7 +144,7 @@ class VInpainter(Inpainter):
         net = _inner_b200(self.net)
         if net is not None:
             return net.inpaint_loop(x_noisy, source, mask, sigmas, alphas, betas, num_resamples,
-                                    progress=progress(), **kwargs)
+                                    progress=progress() if show_progress else None, **kwargs)
         x = x_noisy.float().contiguous().clone()
         src = source.float().expand_as(x).contiguous()
         mask_u8 = mask.expand_as(x).to(torch.uint8).contiguous()
@@ -193,7 +193,8 @@ class VSampler(Sampler):
 
         net = _inner_b200(self.net)
         if net is not None:
-            return net.sample_loop(x_noisy, sigmas, alphas, betas, progress=progress(), **kwargs)
+            return net.sample_loop(x_noisy, sigmas, alphas, betas,
+                                   progress=progress() if show_progress else None, **kwargs)
         ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], 1).float().contiguous()
         x = x_noisy.float().contiguous().clone()
         for i in progress():

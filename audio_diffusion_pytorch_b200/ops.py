@@ -318,6 +318,18 @@ def sampler_step(x: Tensor, v: Tensor, ab: Tensor, x_next: Tensor) -> Tensor:
     return x_next
 
 
+def step_select(step: Tensor, ctrl: Tensor, ab_table: Tensor, ab_out: Tensor, ss_out: Tensor) -> None:
+    """ss_out <- table[step // ctrl[1]], ab_out <- ab_table[step]  (table address in ctrl[0])."""
+    _launch(lambda: _lib.lib().adp_step_select(step.data_ptr(), ctrl.data_ptr(), ab_table.data_ptr(),
+                                               ab_out.data_ptr(), ss_out.data_ptr(), ss_out.numel(), _stream()),
+            "adp_step_select", lambda: ("step_select", 0, 2 * _nb(ss_out)))
+
+
+def step_advance(step: Tensor) -> None:
+    _launch(lambda: _lib.lib().adp_step_advance(step.data_ptr(), _stream()), "adp_step_advance",
+            lambda: ("step_advance", 0, 4))
+
+
 def inpaint_blend(x: Tensor, source: Tensor, noise: Tensor, mask_u8: Tensor, ab: Tensor) -> Tensor:
     """In place: x = ab[2]*source + ab[3]*noise where mask (VInpainter, reference diffusion.py:346-350)."""
     _launch(lambda: _lib.lib().adp_inpaint_blend(x.data_ptr(), source.data_ptr(), noise.data_ptr(),

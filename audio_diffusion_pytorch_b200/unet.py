@@ -241,6 +241,8 @@ class B200UNet(nn.Module):
         # statistics, csrc/mid_conv.cu) instead of three: those levels are HBM-bound
         self.fuse_thin_levels = True
         self.cond_table_rows = 4096    # sampler: rows (steps x batch) of conditioning per pass
+        self.max_table_steps = 4096    # iterations per conditioning block (alpha/beta table rows)
+        self.steps_per_graph = 10      # sampling steps captured back to back in one CUDA graph
 
     # ------------------------------------------------------------------ weights
     def levels(self) -> List[LevelParams]:
@@ -523,6 +525,14 @@ class B200UNet(nn.Module):
             slot_i[0] += 1
             return s
 
+        if mode == "sample":
+            # the step's conditioning rows and alpha/beta are picked ON THE DEVICE from tables by a
+            # step counter, so the captured graph is identical for every step (the host only
+            # replays it, and several steps are captured back to back: _execute_steps)
+            plan.step = torch.zeros(1, dtype=torch.int32, device=dev)
+            plan.ctrl = torch.zeros(2, dtype=torch.int64, device=dev)
+            plan.ab_table = torch.zeros(self.max_table_steps, 4, device=dev)
+            plan.multi_graph, plan.multi_steps = None, 0
         plan.add(lambda: arena.zero_())
 
         # ---- conditioning: f = MLP(GELU(embed(sigma))) (+features); ss = W_all SiLU(f) + b.
@@ -532,6 +542,7 @@ class B200UNet(nn.Module):
             ss_all = torch.zeros(Bh, ops.round_up(P["cond_n"], 8), device=dev)
             plan.ss_all = ss_all
             plan.use_features_in = False
+            plan.add(lambda: ops.step_select(plan.step, plan.ctrl, plan.ab_table, plan.ab, ss_all))
         else:
             ss_all = self._add_conditioning(plan, P, Bh)
         ss_stride = ss_all.shape[1]
@@ -702,6 +713,8 @@ class B200UNet(nn.Module):
                 ops.stem_out(plan.h0, plan.x, L0["up_w"], L0["up_b"], plan.gate0, lv0.factor,
                              v_out=plan.v, **kw)
         plan.add(final)
+        if mode == "sample":
+            plan.add(lambda: ops.step_advance(plan.step))
         plan.workspace_bytes = pool.total_bytes
         assert slot_i[0] <= n_slots
         return plan
@@ -752,6 +765,40 @@ class B200UNet(nn.Module):
             plan.graph = g
             g.replay()
         plan.runs += 1
+
+    def _execute_steps(self, plan: _Plan, n: int) -> None:
+        """n consecutive sampling steps of a 'sample' plan.  Once the single-step graph exists, a
+        second graph holding `steps_per_graph` steps back to back is captured and used for full
+        groups: 5 graph launches instead of 50 per 50-step sample (host-side launch cost and its
+        variance between boxes stay off the critical path)."""
+        S = self.steps_per_graph
+        while n > 0:
+            if (self.use_cuda_graph and S > 1 and n >= S and plan.graph is not None):
+                if plan.multi_graph is None or plan.multi_steps != S:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    _lib.lib().adp_debug_set(2, 1)
+                    try:
+                        with torch.cuda.graph(g):
+                            for _ in range(S):
+                                plan.run_eager()
+                    finally:
+                        _lib.lib().adp_debug_set(2, 0)
+                    plan.multi_graph, plan.multi_steps = g, S
+                plan.multi_graph.replay()
+                plan.runs += S
+                n -= S
+            else:
+                self._execute(plan)
+                n -= 1
+
+    def _set_step_tables(self, plan: _Plan, table: Tensor, ab_rows: Tensor, share: int = 1) -> None:
+        """Points the plan's step selector at a block of conditioning rows [n, Bh, stride] and its
+        alpha/beta rows [n_iterations, 4]; resets the device step counter."""
+        assert ab_rows.shape[0] <= plan.ab_table.shape[0], "too many iterations per conditioning block"
+        plan.ab_table[: ab_rows.shape[0]].copy_(ab_rows, non_blocking=True)
+        plan.ctrl.copy_(torch.tensor([table.data_ptr(), share], dtype=torch.int64), non_blocking=True)
+        plan.step.zero_()
 
     def _stage_inputs(self, plan: _Plan, x: Tensor, time: Optional[Tensor], features, embedding,
                       embedding_scale: float, embedding_mask_proba: float, append_channels):
@@ -846,19 +893,24 @@ class B200UNet(nn.Module):
         num_steps = sigmas.shape[0] - 1
         ab = torch.stack([alphas[:-1], betas[:-1], alphas[1:], betas[1:]], dim=1).float().contiguous()
         sig = sigmas.float().repeat(1, Bh // B).contiguous()      # [N+1, Bh]
-        # conditioning table in blocks of <= ~4096 rows (190 KB of fp32 per row for the README net)
-        block = max(1, self.cond_table_rows // Bh)
-        table, first = None, 0
-        steps = range(num_steps) if progress is None else progress
-        for i in steps:   # two small device copies + one graph launch per step, no host sync
-            if table is None or not (first <= i < first + table.shape[0]):
-                first = (i // block) * block
-                n = min(block, num_steps - first)
-                feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
-                table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
-            plan.ab.copy_(ab[i], non_blocking=True)
-            plan.ss_all.copy_(table[i - first], non_blocking=True)
-            self._execute(plan)
+        # conditioning table in blocks of <= ~4096 rows (190 KB of fp32 per row for the README net);
+        # inside a block the device picks each step's rows: graph launches only, no host sync
+        block = max(1, min(self.cond_table_rows // Bh, self.max_table_steps))
+        it = iter(progress) if progress is not None else None
+        for first in range(0, num_steps, block):
+            n = min(block, num_steps - first)
+            feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
+            table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
+            self._set_step_tables(plan, table, ab[first:first + n])
+            if it is None:
+                self._execute_steps(plan, n)
+            else:                      # progress bar: one graph launch per step
+                for _ in range(n):
+                    next(it)
+                    self._execute(plan)
+        if it is not None:
+            for _ in it:               # let the progress generator finish (last description update)
+                pass
         return plan.x.clone().to(x_noisy.dtype)
 
 
@@ -888,20 +940,27 @@ def _inpaint_loop(self, x_noisy: Tensor, source: Tensor, mask: Tensor, sigmas: T
     sig = sigmas.float().repeat(1, Bh // B).contiguous()
     src = source.float().expand_as(plan.x).contiguous()
     mask_u8 = mask.expand_as(plan.x).to(torch.uint8).contiguous()
-    block = max(1, self.cond_table_rows // Bh)
-    table, first = None, 0
-    for i in (range(num_steps) if progress is None else progress):
-        if table is None or not (first <= i < first + table.shape[0]):
-            first = (i // block) * block
-            n = min(block, num_steps - first)
-            feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
-            table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
-        plan.ss_all.copy_(table[i - first], non_blocking=True)
-        for r in range(num_resamples):
-            plan.ab.copy_(ab[i, int(r == num_resamples - 1)], non_blocking=True)
-            self._execute(plan)
-            ops.inpaint_blend(plan.x, src, torch.randn_like(source).float().expand_as(plan.x).contiguous(),
-                              mask_u8, plan.ab)
+    block = max(1, min(self.cond_table_rows // Bh, self.max_table_steps // max(1, num_resamples)))
+    # per iteration (step i, resample r): alpha/beta row = ab[i][r is the last]
+    last = torch.zeros(num_resamples, dtype=torch.long, device=ab.device)
+    last[-1] = 1
+    it = iter(progress) if progress is not None else None
+    for first in range(0, num_steps, block):
+        n = min(block, num_steps - first)
+        feats = plan.features_in.repeat(n, 1) if plan.use_features_in else None
+        table = self._cond_table(sig[first:first + n].reshape(-1), feats).view(n, Bh, -1)
+        ab_rows = ab[first:first + n][:, last].reshape(n * num_resamples, 4)
+        self._set_step_tables(plan, table, ab_rows, share=num_resamples)
+        for _ in range(n):
+            if it is not None:
+                next(it)
+            for r in range(num_resamples):
+                self._execute(plan)
+                ops.inpaint_blend(plan.x, src, torch.randn_like(source).float().expand_as(plan.x).contiguous(),
+                                  mask_u8, plan.ab)
+    if it is not None:
+        for _ in it:
+            pass
     return plan.x.clone().to(x_noisy.dtype)
 
 
