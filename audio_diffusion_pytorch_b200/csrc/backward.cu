@@ -528,7 +528,7 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
     }
 #pragma unroll
     for (int bb = 0; bb < kCondMaxB; ++bb)
-      if (bb < B) {
+      if (bb < B && dcond != nullptr) {
         float* dp = dcond + static_cast<size_t>(bb) * K + k4;
         atomicAdd(dp, dc[bb].x); atomicAdd(dp + 1, dc[bb].y);
         atomicAdd(dp + 2, dc[bb].z); atomicAdd(dp + 3, dc[bb].w);
@@ -651,7 +651,7 @@ extern "C" int adp_skip_gate_bwd(const void* dout, const void* y, const float* g
 extern "C" int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond, const void* w,
                             float* dw, float* dbias, float* dcond, int32_t B, int32_t N, int32_t K,
                             adp_stream_t stream) {
-  ADP_CHECK(dss && cond && w && dw && dbias && dcond, "adp_cond_bwd: null");
+  ADP_CHECK(dss && cond && w && dw && dbias, "adp_cond_bwd: null");   // dcond may be NULL (not wanted)
   ADP_CHECK(B >= 1, "adp_cond_bwd: B=%d", B);
   const int rows_per_block = 64;
   static SmemAttrCache smem_cache;
@@ -665,7 +665,7 @@ extern "C" int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond,
     ADP_CUDA(launch_k(cond_bwd_kernel, grid, dim3(256), smem, as_stream(stream),
                       dss + static_cast<size_t>(b0) * ld_dss, (int)ld_dss,
                       cond + static_cast<size_t>(b0) * K, static_cast<const __nv_bfloat16*>(w), dw,
-                      dbias, dcond + static_cast<size_t>(b0) * K, (int)bc, (int)N, (int)K,
+                      dbias, dcond ? dcond + static_cast<size_t>(b0) * K : nullptr, (int)bc, (int)N, (int)K,
                       (int)rows_per_block, (int)(b0 > 0)));
   }
   return 0;

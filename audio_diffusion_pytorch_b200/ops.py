@@ -425,12 +425,12 @@ def skip_gate_bwd(dout: Tensor, y: Tensor, gate: Tensor, dys: Tensor, dgate: Ten
     return dys
 
 
-def cond_bwd(dss: Tensor, cond: Tensor, w: Tensor, dw: Tensor, dbias: Tensor, dcond: Tensor,
+def cond_bwd(dss: Tensor, cond: Tensor, w: Tensor, dw: Tensor, dbias: Tensor, dcond: Optional[Tensor],
              N: int) -> None:
     B, K = cond.shape
     _launch(lambda: _lib.lib().adp_cond_bwd(dss.data_ptr(), dss.stride(0), cond.data_ptr(),
                                             w.data_ptr(), dw.data_ptr(), dbias.data_ptr(),
-                                            dcond.data_ptr(), B, N, K, _stream()),
+                                            _p(dcond), B, N, K, _stream()),
             "adp_cond_bwd", lambda: (f"cond_bwd[B={B} N={N} K={K}]", 4.0 * B * N * K, N * K * 6))
 
 

@@ -152,8 +152,8 @@ class GradSync:
         cond_g = torch.empty(self.world * B, Fm, device=plan.dss_all.device)
         dist.all_gather_into_tensor(dss_g, plan.dss_all.contiguous(), group=self.group)
         dist.all_gather_into_tensor(cond_g, plan.cond_bf.view(B, Fm).float(), group=self.group)
-        scratch = torch.zeros(self.world * B, Fm, device=plan.dss_all.device)
-        ops.cond_bwd(dss_g, cond_g, plan.P["cond_w"], plan.dw_all, plan.dbias_all, scratch, plan.n_tot)
+        # d cond is a local quantity (already computed by the backward program): not wanted here
+        ops.cond_bwd(dss_g, cond_g, plan.P["cond_w"], plan.dw_all, plan.dbias_all, None, plan.n_tot)
         plan.dw_all.div_(self.world)
         plan.dbias_all.div_(self.world)
 

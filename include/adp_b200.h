@@ -291,7 +291,8 @@ int adp_skip_gate_bwd(const void* dout, const void* y, const float* gate, int32_
                       void* dys, float* dgate, int32_t ld_dgate, int32_t B, int32_t T, int32_t C,
                       adp_stream_t stream);
 /* Backward of the concatenated conditioning projection ss = cond W^T + b:
- * dw[n][k] = sum_b dss[b][n]*cond[b][k]; dbias[n] = sum_b dss[b][n]; dcond += dss W. */
+ * dw[n][k] = sum_b dss[b][n]*cond[b][k]; dbias[n] = sum_b dss[b][n]; dcond += dss W
+ * (dcond may be NULL when only the parameter gradients are wanted). */
 int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond, const void* w, float* dw,
                  float* dbias, float* dcond, int32_t B, int32_t N, int32_t K, adp_stream_t stream);
 
