@@ -479,7 +479,9 @@ skip_gate_bwd_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ y
 //   dcond[b][k] += sum_n dss[b][n]*W[n][k]
 // Pure streaming (W read once as bf16, dW written once as fp32): every thread owns 4 consecutive
 // k, so W arrives as 8-byte and dW leaves as 16-byte vectors; cond[.][k..k+3] stays in registers.
-constexpr int kCondMaxB = 8;          // batch rows per pass (the launcher loops over larger batches)
+constexpr int kCondMaxB = 8;          // batch rows per pass of the in-graph (local) call
+constexpr int kCondGatherB = 32;      // ... of the data-parallel call on all-gathered rows (no dcond)
+template <int MAXB, bool DC>
 __global__ void __launch_bounds__(256)
 cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restrict__ cond,
                 const __nv_bfloat16* __restrict__ w, float* __restrict__ dw,
@@ -487,10 +489,10 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
                 int rows_per_block, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_d[];       // dss slab [B][rows_per_block]
+  extern __shared__ float s_d[];       // dss slab [MAXB][rows_per_block], zero beyond B
   const int n0 = blockIdx.x * rows_per_block;
   const int nr = min(rows_per_block, N - n0);
-  for (int i = threadIdx.x; i < kCondMaxB * rows_per_block; i += blockDim.x) {
+  for (int i = threadIdx.x; i < MAXB * rows_per_block; i += blockDim.x) {
     const int bb = i / rows_per_block, r = i - bb * rows_per_block;
     s_d[i] = (bb < B && r < nr) ? dss[static_cast<size_t>(bb) * ld_dss + n0 + r] : 0.f;
   }
@@ -501,23 +503,25 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
     dbias[n0 + threadIdx.x] = accumulate ? dbias[n0 + threadIdx.x] + t : t;
   }
   for (int k4 = threadIdx.x * 4; k4 < K; k4 += blockDim.x * 4) {
-    float4 c4[kCondMaxB], dc[kCondMaxB];
+    float4 c4[MAXB], dc[DC ? MAXB : 1];
 #pragma unroll
-    for (int bb = 0; bb < kCondMaxB; ++bb) {
+    for (int bb = 0; bb < MAXB; ++bb) {
       c4[bb] = bb < B ? *reinterpret_cast<const float4*>(cond + static_cast<size_t>(bb) * K + k4)
                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      dc[bb] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (DC) dc[bb] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int r = 0; r < nr; ++r) {
       const uint2 wu = __ldg(reinterpret_cast<const uint2*>(w + static_cast<size_t>(n0 + r) * K + k4));
       const float2 w01 = unpack_bf16(wu.x), w23 = unpack_bf16(wu.y);
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int bb = 0; bb < kCondMaxB; ++bb) {
+      for (int bb = 0; bb < MAXB; ++bb) {
         const float d = s_d[bb * rows_per_block + r];       // zero rows beyond B: no branch needed
         g.x += d * c4[bb].x; g.y += d * c4[bb].y; g.z += d * c4[bb].z; g.w += d * c4[bb].w;
-        dc[bb].x += d * w01.x; dc[bb].y += d * w01.y; dc[bb].z += d * w23.x; dc[bb].w += d * w23.y;
+        if constexpr (DC) {
+          dc[bb].x += d * w01.x; dc[bb].y += d * w01.y; dc[bb].z += d * w23.x; dc[bb].w += d * w23.y;
+        }
       }
       float4* dwp = reinterpret_cast<float4*>(dw + static_cast<size_t>(n0 + r) * K + k4);
       if (accumulate) {
@@ -526,13 +530,15 @@ cond_bwd_kernel(const float* __restrict__ dss, int ld_dss, const float* __restri
       }
       *dwp = g;
     }
+    if constexpr (DC) {
 #pragma unroll
-    for (int bb = 0; bb < kCondMaxB; ++bb)
-      if (bb < B && dcond != nullptr) {
-        float* dp = dcond + static_cast<size_t>(bb) * K + k4;
-        atomicAdd(dp, dc[bb].x); atomicAdd(dp + 1, dc[bb].y);
-        atomicAdd(dp + 2, dc[bb].z); atomicAdd(dp + 3, dc[bb].w);
-      }
+      for (int bb = 0; bb < MAXB; ++bb)
+        if (bb < B) {
+          float* dp = dcond + static_cast<size_t>(bb) * K + k4;
+          atomicAdd(dp, dc[bb].x); atomicAdd(dp + 1, dc[bb].y);
+          atomicAdd(dp + 2, dc[bb].z); atomicAdd(dp + 3, dc[bb].w);
+        }
+    }
   }
 }
 
@@ -648,25 +654,34 @@ extern "C" int adp_skip_gate_bwd(const void* dout, const void* y, const float* g
   return 0;
 }
 
+template <int MAXB, bool DC>
+static int launch_cond_bwd(const float* dss, int ld_dss, const float* cond, const void* w, float* dw,
+                           float* dbias, float* dcond, int B, int N, int K, cudaStream_t stream) {
+  const int rows_per_block = 64;
+  static SmemAttrCache smem_cache;
+  dim3 grid((N + rows_per_block - 1) / rows_per_block);
+  const size_t smem = static_cast<size_t>(MAXB) * rows_per_block * sizeof(float);
+  ADP_CUDA(ensure_dyn_smem(cond_bwd_kernel<MAXB, DC>, smem, smem_cache));
+  // batches beyond MAXB rows run as further passes that accumulate into dw / dbias
+  for (int b0 = 0; b0 < B; b0 += MAXB) {
+    const int bc = B - b0 < MAXB ? B - b0 : MAXB;
+    ADP_CUDA(launch_k(cond_bwd_kernel<MAXB, DC>, grid, dim3(256), smem, stream,
+                      dss + static_cast<size_t>(b0) * ld_dss, ld_dss, cond + static_cast<size_t>(b0) * K,
+                      static_cast<const __nv_bfloat16*>(w), dw, dbias,
+                      dcond ? dcond + static_cast<size_t>(b0) * K : nullptr, bc, N, K, rows_per_block,
+                      (int)(b0 > 0)));
+  }
+  return 0;
+}
+
 extern "C" int adp_cond_bwd(const float* dss, int32_t ld_dss, const float* cond, const void* w,
                             float* dw, float* dbias, float* dcond, int32_t B, int32_t N, int32_t K,
                             adp_stream_t stream) {
   ADP_CHECK(dss && cond && w && dw && dbias, "adp_cond_bwd: null");   // dcond may be NULL (not wanted)
   ADP_CHECK(B >= 1, "adp_cond_bwd: B=%d", B);
-  const int rows_per_block = 64;
-  static SmemAttrCache smem_cache;
-  dim3 grid((N + rows_per_block - 1) / rows_per_block);
-  // batches beyond kCondMaxB rows run as further passes that accumulate into dw / dbias
   ADP_CHECK(K % 4 == 0, "adp_cond_bwd: K=%d must be a multiple of 4", K);
-  for (int b0 = 0; b0 < B; b0 += kCondMaxB) {
-    const int bc = B - b0 < kCondMaxB ? B - b0 : kCondMaxB;
-    const size_t smem = static_cast<size_t>(kCondMaxB) * rows_per_block * sizeof(float);
-    ADP_CUDA(ensure_dyn_smem(cond_bwd_kernel, smem, smem_cache));
-    ADP_CUDA(launch_k(cond_bwd_kernel, grid, dim3(256), smem, as_stream(stream),
-                      dss + static_cast<size_t>(b0) * ld_dss, (int)ld_dss,
-                      cond + static_cast<size_t>(b0) * K, static_cast<const __nv_bfloat16*>(w), dw,
-                      dbias, dcond ? dcond + static_cast<size_t>(b0) * K : nullptr, (int)bc, (int)N, (int)K,
-                      (int)rows_per_block, (int)(b0 > 0)));
-  }
-  return 0;
+  cudaStream_t s = as_stream(stream);
+  if (dcond == nullptr)       // parameter gradients only (all-gathered rows of a data-parallel step):
+    return launch_cond_bwd<kCondGatherB, false>(dss, ld_dss, cond, w, dw, dbias, nullptr, B, N, K, s);
+  return launch_cond_bwd<kCondMaxB, true>(dss, ld_dss, cond, w, dw, dbias, dcond, B, N, K, s);
 }
