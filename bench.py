@@ -392,70 +392,72 @@ def main():
     value = clips * CLIP_SECONDS / (ms_per_step * 1e-3)
     e2e_value = clips * CLIP_SECONDS / (e2e_ms / args.steps * 1e-3)
 
-    # ---- roofline of the dominant kernel/shape of one net evaluation.
-    # (1) in-graph durations per kernel + shape: the step's CUDA graph re-captured with programmatic
-    #     dependent launch OFF (with PDL a kernel's duration includes the time it waits for its
-    #     predecessor) and replayed under CUPTI activity tracing, AFTER the timed region;
-    # (2) the same launches timed with CUDA events in an eager pass of the plan (upper bound:
-    #     includes host launch gaps).  `achieved` uses (1); (2) is reported next to it.
-    from audio_diffusion_pytorch_b200 import _lib
+    roof, table = None, {}
     plan = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
     cond_plan = next((p for k, p in net._plans.items() if k[0] == "cond"), None)
     n_kernels, n_pre = plan.n_kernels, len(getattr(plan, "pre", []))
-    table = net.profile_plan(plan, iters=5)
-    hbm, tf_burst, tf_sust, which = peaks()
-    gtab, busy_us, in_graph_err = None, None, None
-    try:
-        from tools.graph_profile import in_graph_table
-        saved = dict(net._plans)
-        net._plans.clear()
-        _lib.lib().adp_debug_set(6, 0)
+    if rank == 0:      # profiling passes (no collectives inside): rank 0 only
+        # ---- roofline of the dominant kernel/shape of one net evaluation.
+        # (1) in-graph durations per kernel + shape: the step's CUDA graph re-captured with programmatic
+        #     dependent launch OFF (with PDL a kernel's duration includes the time it waits for its
+        #     predecessor) and replayed under CUPTI activity tracing, AFTER the timed region;
+        # (2) the same launches timed with CUDA events in an eager pass of the plan (upper bound:
+        #     includes host launch gaps).  `achieved` uses (1); (2) is reported next to it.
+        from audio_diffusion_pytorch_b200 import _lib
+        table = net.profile_plan(plan, iters=5)
+        hbm, tf_burst, tf_sust, which = peaks()
+        gtab, busy_us, in_graph_err = None, None, None
         try:
-            for _ in range(2):
-                model.sample(dev_in, num_steps=2, **dev_kw, **kw)
-            plan_np = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
-            gtab, _, busy_us, _ = in_graph_table(
-                net, plan_np, lambda k: model.sample(dev_in, num_steps=k, **dev_kw, **kw), 4)
-        finally:
-            _lib.lib().adp_debug_set(6, 1)
+            from tools.graph_profile import in_graph_table
+            saved = dict(net._plans)
             net._plans.clear()
-            net._plans.update(saved)
-    except Exception as exc:                      # profiler unavailable: event-timed numbers only
-        in_graph_err = repr(exc)[:200]
-    if gtab:
-        top_name = max(gtab, key=lambda k: gtab[k]["us_total"])
-        top_us, top_share = gtab[top_name]["us_avg"], gtab[top_name]["us_total"] / busy_us
-        top = table.get(top_name) or {"name": top_name, "flops": gtab[top_name]["flops"],
-                                      "bytes": gtab[top_name]["bytes"], "count": gtab[top_name]["count"],
-                                      "ms_avg": float("nan"), "ms_total": float("nan")}
-    else:
-        top = max(table.values(), key=lambda r: r["ms_total"])
-        top_us = top["ms_avg"] * 1e3
-        top_share = top["ms_total"] / sum(r["ms_total"] for r in table.values())
-    ai = top["flops"] / max(top["bytes"], 1)
-    tensor_bound = ai >= tf_sust * 1e12 / (hbm * 1e9)
-    work, peak, unit = ((top["flops"] / 1e6, tf_sust, "TFLOP/s") if tensor_bound
-                        else (top["bytes"] / 1e3, hbm, "GB/s"))
-    achieved = work / top_us
-    roof = {"bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
-            "frac": achieved / peak, "kernel_us": top_us,
-            "timing": ("in-graph (CUDA graph of the step re-captured with PDL off, CUPTI activity records, "
-                       "4 steps averaged)" if gtab else "CUDA events around each launch of an eager pass"),
-            "achieved_eager_events": work / (top["ms_avg"] * 1e3), "eager_event_us": top["ms_avg"] * 1e3}
-    if in_graph_err:
-        roof["in_graph_error"] = in_graph_err
-    if busy_us is not None:
-        roof["kernel_busy_us_per_net_eval"] = busy_us
-    traffic, traffic_src = ncu_traffic(top["name"])
-    roof.update({"kernel": top["name"], "launches_per_net_eval": top["count"],
-                 "share_of_step": top_share, "peak_source": which,
-                 "traffic": traffic, "traffic_source": traffic_src,
-                 "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"]})
-    # whole-step roofline: sum over levels of max(flop time, byte time)
-    t_bound = sum(max(r["flops"] / (tf_sust * 1e12), r["bytes"] / (hbm * 1e9)) * r["count"]
-                  for r in table.values())
-    roof["step_bound_ms"] = t_bound * 1e3
-    roof["step_frac"] = t_bound * 1e3 / (ms_per_step / num_steps)
+            _lib.lib().adp_debug_set(6, 0)
+            try:
+                for _ in range(2):
+                    model.sample(dev_in, num_steps=2, **dev_kw, **kw)
+                plan_np = next(p for k, p in net._plans.items() if len(k) > 4 and k[4] == "sample")
+                gtab, _, busy_us, _ = in_graph_table(
+                    net, plan_np, lambda k: model.sample(dev_in, num_steps=k, **dev_kw, **kw), 4)
+            finally:
+                _lib.lib().adp_debug_set(6, 1)
+                net._plans.clear()
+                net._plans.update(saved)
+        except Exception as exc:                      # profiler unavailable: event-timed numbers only
+            in_graph_err = repr(exc)[:200]
+        if gtab:
+            top_name = max(gtab, key=lambda k: gtab[k]["us_total"])
+            top_us, top_share = gtab[top_name]["us_avg"], gtab[top_name]["us_total"] / busy_us
+            top = table.get(top_name) or {"name": top_name, "flops": gtab[top_name]["flops"],
+                                          "bytes": gtab[top_name]["bytes"], "count": gtab[top_name]["count"],
+                                          "ms_avg": float("nan"), "ms_total": float("nan")}
+        else:
+            top = max(table.values(), key=lambda r: r["ms_total"])
+            top_us = top["ms_avg"] * 1e3
+            top_share = top["ms_total"] / sum(r["ms_total"] for r in table.values())
+        ai = top["flops"] / max(top["bytes"], 1)
+        tensor_bound = ai >= tf_sust * 1e12 / (hbm * 1e9)
+        work, peak, unit = ((top["flops"] / 1e6, tf_sust, "TFLOP/s") if tensor_bound
+                            else (top["bytes"] / 1e3, hbm, "GB/s"))
+        achieved = work / top_us
+        roof = {"bound": "tensor" if tensor_bound else "hbm", "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak, "kernel_us": top_us,
+                "timing": ("in-graph (CUDA graph of the step re-captured with PDL off, CUPTI activity records, "
+                           "4 steps averaged)" if gtab else "CUDA events around each launch of an eager pass"),
+                "achieved_eager_events": work / (top["ms_avg"] * 1e3), "eager_event_us": top["ms_avg"] * 1e3}
+        if in_graph_err:
+            roof["in_graph_error"] = in_graph_err
+        if busy_us is not None:
+            roof["kernel_busy_us_per_net_eval"] = busy_us
+        traffic, traffic_src = ncu_traffic(top["name"])
+        roof.update({"kernel": top["name"], "launches_per_net_eval": top["count"],
+                     "share_of_step": top_share, "peak_source": which,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "flops_per_launch": top["flops"], "bytes_per_launch": top["bytes"]})
+        # whole-step roofline: sum over levels of max(flop time, byte time)
+        t_bound = sum(max(r["flops"] / (tf_sust * 1e12), r["bytes"] / (hbm * 1e9)) * r["count"]
+                      for r in table.values())
+        roof["step_bound_ms"] = t_bound * 1e3
+        roof["step_frac"] = t_bound * 1e3 / (ms_per_step / num_steps)
     if args.profile_ops and rank == 0:
         for r in sorted(table.values(), key=lambda r: -r["ms_total"]):
             print(f"# {r['name']:58s} x{r['count']:3d} avg {r['ms_avg'] * 1e3:8.1f} us  "
