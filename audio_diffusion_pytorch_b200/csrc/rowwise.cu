@@ -465,15 +465,18 @@ __global__ void sampler_step_kernel(const float* __restrict__ x, const float* __
 // Per-step inputs of the captured sampling step, selected ON THE DEVICE: the step graph is the same
 // for every step (and several steps can be captured back to back), the host only replays it.
 //   ctrl[0] = address of the conditioning table rows [n][ss_elems] (fp32), ctrl[1] = steps that
-//   share one table row (VInpainter resamples), step = iterations done since the host reset it
+//   share one table row (VInpainter resamples), ctrl[2] = n (rows; the index is clamped to it, so a
+//   replay past the end of the block re-uses the last row instead of reading out of bounds),
+//   step = iterations done since the host reset it
 __global__ void step_select_kernel(const int* __restrict__ step, const long long* __restrict__ ctrl,
                                    const float* __restrict__ ab_table, float* __restrict__ ab_out,
                                    float* __restrict__ ss_out, int64_t ss_elems) {
   pdl_launch_dependents();
   pdl_wait();
-  const int it = *step;
   const float* table = reinterpret_cast<const float*>(ctrl[0]);
   const long long div = ctrl[1] > 0 ? ctrl[1] : 1;
+  const long long n_it = (ctrl[2] > 0 ? ctrl[2] : 1) * div;
+  const long long it = *step < n_it ? *step : n_it - 1;
   const float4* src = reinterpret_cast<const float4*>(table + static_cast<size_t>(it / div) * ss_elems);
   float4* dst = reinterpret_cast<float4*>(ss_out);
   const int64_t n4 = ss_elems >> 2;

@@ -530,7 +530,7 @@ class B200UNet(nn.Module):
             # step counter, so the captured graph is identical for every step (the host only
             # replays it, and several steps are captured back to back: _execute_steps)
             plan.step = torch.zeros(1, dtype=torch.int32, device=dev)
-            plan.ctrl = torch.zeros(2, dtype=torch.int64, device=dev)
+            plan.ctrl = torch.zeros(3, dtype=torch.int64, device=dev)
             plan.ab_table = torch.zeros(self.max_table_steps, 4, device=dev)
             plan.multi_graph, plan.multi_steps = None, 0
         plan.add(lambda: arena.zero_())
@@ -734,6 +734,8 @@ class B200UNet(nn.Module):
         per kernel/shape -> {label: count per pass, avg/total ms per pass, flops, bytes}."""
         with ops.trace(timing=True) as tr:
             for _ in range(iters):
+                if hasattr(plan, "step"):
+                    plan.step.zero_()
                 plan.run_eager()
         table = tr.table()
         for row in table.values():
@@ -797,7 +799,8 @@ class B200UNet(nn.Module):
         alpha/beta rows [n_iterations, 4]; resets the device step counter."""
         assert ab_rows.shape[0] <= plan.ab_table.shape[0], "too many iterations per conditioning block"
         plan.ab_table[: ab_rows.shape[0]].copy_(ab_rows, non_blocking=True)
-        plan.ctrl.copy_(torch.tensor([table.data_ptr(), share], dtype=torch.int64), non_blocking=True)
+        plan.ctrl.copy_(torch.tensor([table.data_ptr(), share, table.shape[0]], dtype=torch.int64),
+                        non_blocking=True)
         plan.step.zero_()
 
     def _stage_inputs(self, plan: _Plan, x: Tensor, time: Optional[Tensor], features, embedding,

@@ -223,7 +223,7 @@ int adp_sampler_step(const float* x, const float* v, const float* ab, float* x_n
 /* The sampling loop's per-step inputs selected on the device (reference diffusion.py:183-187 indexes
  * sigmas[i], alphas[i], betas[i] on the host): step[0] = iterations done since the host reset it,
  * ctrl[0] = device address of the conditioning table rows fp32 [n][ss_elems], ctrl[1] = iterations
- * sharing one table row (VInpainter resamples; 0/1 = one).  Copies row step/ctrl[1] to ss_out and
+ * sharing one table row (VInpainter resamples; 0/1 = one), ctrl[2] = n (the row index is clamped).  Copies row step/ctrl[1] to ss_out and
  * ab_table[step][0..3] to ab_out, so ONE captured graph serves every step and several steps can be
  * captured back to back.  adp_step_advance: step[0] += 1 (last launch of a step). */
 int adp_step_select(const int32_t* step, const int64_t* ctrl, const float* ab_table, float* ab_out,

@@ -22,6 +22,8 @@ def in_graph_table(net, plan, run_steps, steps: int):
     Returns ({label: {count, us_avg, us_total, flops, bytes}} per step, kernels per step,
     kernel-busy us per step, span us per step)."""
     from audio_diffusion_pytorch_b200 import ops
+    if hasattr(plan, "step"):
+        plan.step.zero_()
     with ops.trace() as tr:
         plan.run_eager()
     torch.cuda.synchronize()
