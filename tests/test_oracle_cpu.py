@@ -118,3 +118,57 @@ def test_vocoder_sample_and_loss(oracle_port, golden_dir):
     torch.manual_seed(9)
     loss = m(t(g["audio"]))
     assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+# ------------------------------------------------------------------ round-2 golden vectors
+def test_oracle_50_step_sampler_and_inpainter(oracle_port, golden_dir):
+    """tiny_sample50.npz / tiny_inpaint.npz (oracle/make_golden_r2.py): the headline metric is a
+    50-step sample; VInpainter consumes torch.randn_like draws in a fixed order."""
+    g = load(golden_dir, "tiny_sample50.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(**TINY)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    noise = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["noise_seed"])))
+    assert rel_l2(m.sample(noise, num_steps=50), t(g["sample50"])) <= 20 * RTOL   # 50 steps compound
+
+    g = load(golden_dir, "tiny_inpaint.npz")
+    source = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["source_seed"])))
+    mask = torch.zeros(2, 2, 4096, dtype=torch.bool)
+    for b_, lo, hi in g["mask_spans"]:
+        mask[b_, :, lo:hi] = True
+    torch.manual_seed(int(g["rng_seed"]))
+    out = oracle_port.VInpainterPort(net=m.net)(source, mask, num_steps=int(g["num_steps"]),
+                                                num_resamples=int(g["num_resamples"]))
+    assert rel_l2(out, t(g["out"])) <= 10 * RTOL
+    assert torch.equal(out[mask], source[mask])        # sigma = 0 at the end: the known region is the source
+
+
+def test_oracle_readme_scale_goldens(oracle_port, golden_dir):
+    """readme_full_size.npz (forward at [1,2,2^18], windows) and cfg3_readme_scale.npz (text +
+    guidance at README scale): the oracle re-evaluated on this machine's CPU."""
+    README = dict(in_channels=2, channels=[8, 32, 64, 128, 256, 512, 512, 1024, 1024],
+                  factors=[1, 4, 4, 4, 2, 2, 2, 2, 2], items=[1, 2, 2, 2, 2, 2, 2, 4, 4],
+                  attentions=[0, 0, 0, 0, 0, 1, 1, 1, 1], attention_heads=8, attention_features=64)
+    g = load(golden_dir, "readme_full_size.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(**README)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    x = torch.randn(1, 2, 2 ** 18, generator=torch.Generator().manual_seed(int(g["x_seed"])))
+    with torch.no_grad():
+        v = m.net(x, t(g["sigma"]))
+    win = torch.stack([v[..., int(s):int(s) + 1024] for s in g["starts"]], dim=-2)
+    assert rel_l2(win, t(g["v_windows"])) <= RTOL
+    del m
+
+    g = load(golden_dir, "cfg3_readme_scale.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(**dict(README, cross_attentions=[0, 0, 0, 1, 1, 1, 1, 1, 1],
+                                              use_embedding_cfg=True, embedding_max_length=64,
+                                              embedding_features=768))
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    x = torch.randn(1, 2, int(g["length"]), generator=gen)
+    emb = torch.randn(1, 64, 768, generator=gen)
+    with torch.no_grad():
+        v5 = m.net(x, t(g["sigma"]), embedding=emb, embedding_scale=5.0)
+    assert rel_l2(v5, t(g["v_scale5"])) <= RTOL
