@@ -6,7 +6,8 @@ running something else."""
 from .components import AppendChannelsPlugin, MelSpectrogram, UNetV0
 from .diffusion import (Diffusion, Distribution, Inpainter, LinearSchedule, Sampler, Schedule,
                         UniformDistribution, VDiffusion, VInpainter, VSampler)
-from .models import DiffusionModel, DiffusionUpsampler, DiffusionVocoder
+from .models import (AdapterBase, DiffusionAE, DiffusionModel, DiffusionUpsampler, DiffusionVocoder,
+                     EncoderBase)
 from .unet import B200UNet
 
 
@@ -21,11 +22,9 @@ def _out_of_scope(name: str, why: str):
 
 XUNet = B200UNet
 LTPlugin = _out_of_scope("LTPlugin", "not used by any model class or config")
-DiffusionAE = _out_of_scope("DiffusionAE", "needs the external audio_encoders_pytorch package")
 DiffusionAR = _out_of_scope("DiffusionAR", "use_modulation=False / SkipCat path, SURVEY.md 8f item 1")
-EncoderBase = _out_of_scope("EncoderBase", "DiffusionAE only")
 
 __all__ = ["UNetV0", "XUNet", "LTPlugin", "MelSpectrogram", "VDiffusion", "VSampler", "VInpainter",
            "LinearSchedule", "UniformDistribution", "Diffusion", "Distribution", "Sampler",
            "Schedule", "DiffusionModel", "DiffusionUpsampler", "DiffusionVocoder", "DiffusionAE",
-           "DiffusionAR", "EncoderBase", "AppendChannelsPlugin", "B200UNet", "Inpainter"]
+           "DiffusionAR", "EncoderBase", "AdapterBase", "AppendChannelsPlugin", "B200UNet", "Inpainter"]

@@ -4,7 +4,8 @@ models.py:22-45 (DiffusionModel), :134-165 (DiffusionUpsampler), :168-224 (Diffu
 the arithmetic behind `net`, `diffusion` and `sampler` is the B200 path.  U-Net weights of a
 reference model are taken over with `model.net.load_reference_parameters(ref_model.net)`
 (same parameter order and shapes as a_unet's module tree)."""
-from typing import Callable, Optional, Tuple
+from abc import ABC, abstractmethod
+from typing import Any, Callable, Optional, Sequence, Tuple, Union
 
 import torch
 import torch.nn.functional as F
@@ -13,7 +14,7 @@ from torch import Generator, Tensor, nn
 from .components import AppendChannelsPlugin, MelSpectrogram
 from .diffusion import VDiffusion, VSampler
 from .unet import UNetV0
-from .utils import default, downsample, groupby, randn_like, upsample
+from .utils import closest_power_2, default, downsample, groupby, randn_like, upsample
 
 
 class DiffusionModel(nn.Module):
@@ -37,6 +38,66 @@ class DiffusionModel(nn.Module):
     @torch.no_grad()
     def sample(self, *args, **kwargs) -> Tensor:
         return self.sampler(*args, **kwargs)
+
+
+class EncoderBase(nn.Module, ABC):
+    """What DiffusionAE needs from an encoder: `out_channels`, `downsample_factor` and
+    `forward(x, with_info=True) -> (latent, info)` (reference models.py:48-55)."""
+
+    @abstractmethod
+    def __init__(self):
+        super().__init__()
+        self.out_channels = None
+        self.downsample_factor = None
+
+
+class AdapterBase(nn.Module, ABC):
+    """Optional fixed transform around the diffusion domain (reference models.py:58-67)."""
+
+    @abstractmethod
+    def encode(self, x: Tensor) -> Tensor:
+        pass
+
+    @abstractmethod
+    def decode(self, x: Tensor) -> Tensor:
+        pass
+
+
+class DiffusionAE(DiffusionModel):
+    """Diffusion autoencoder (reference models.py:70-131): the encoder's latent is injected at
+    `inject_depth` of the U-Net (`InjectChannelsItem`: conv1x1 over cat([x, latent]) + x); training
+    back-propagates into the encoder through the context gradient of the B200 backward program."""
+
+    def __init__(self, in_channels: int, channels: Sequence[int], encoder: nn.Module, inject_depth: int,
+                 latent_factor: Optional[int] = None, adapter: Optional[nn.Module] = None, **kwargs):
+        context_channels = [0] * len(channels)
+        context_channels[inject_depth] = encoder.out_channels
+        super().__init__(in_channels=in_channels, channels=channels, context_channels=context_channels,
+                         **kwargs)
+        self.in_channels = in_channels
+        self.encoder = encoder
+        self.inject_depth = inject_depth
+        self.latent_factor = default(latent_factor, self.encoder.downsample_factor)
+        self.adapter = adapter.requires_grad_(False) if adapter is not None else None
+
+    def forward(self, x: Tensor, with_info: bool = False, **kwargs) -> Union[Tensor, Tuple[Tensor, Any]]:
+        latent, info = self.encode(x, with_info=True)
+        context = [None] * self.inject_depth + [latent]
+        x = self.adapter.encode(x) if self.adapter is not None else x
+        loss = super().forward(x, channels=context, **kwargs)
+        return (loss, info) if with_info else loss
+
+    def encode(self, *args, **kwargs):
+        return self.encoder(*args, **kwargs)
+
+    @torch.no_grad()
+    def decode(self, latent: Tensor, generator: Optional[Generator] = None, **kwargs) -> Tensor:
+        length = closest_power_2(latent.shape[2] * self.latent_factor)
+        noise = torch.randn((latent.shape[0], self.in_channels, length), device=latent.device,
+                            dtype=latent.dtype, generator=generator)
+        context = [None] * self.inject_depth + [latent]
+        out = super().sample(noise, channels=context, **kwargs)
+        return self.adapter.decode(out) if self.adapter is not None else out
 
 
 class DiffusionUpsampler(DiffusionModel):

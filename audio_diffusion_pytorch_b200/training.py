@@ -91,10 +91,17 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
     E = net.embedding_features
     plan.embedding = torch.zeros(B, M, E, dtype=bf16, device=dev) if M else None
     plan.demb = torch.zeros(B, M, E, dtype=bf16, device=dev) if M else None
+    # InjectChannelsItem context per depth (channels-last bf16, channels zero-padded to 16) + gradient
+    plan.ctx, plan.dctx, t_l = {}, {}, T
+    for i, c in enumerate(net.context_channels):
+        t_l //= net.factors[i]
+        if c > 0:
+            plan.ctx[i] = torch.zeros(B, t_l, ops.round_up(c, 16), dtype=bf16, device=dev)
+            plan.dctx[i] = torch.zeros(B, t_l, ops.round_up(c, 16), dtype=bf16, device=dev)
 
     # ---- statistics + gradient arenas
     n_items = sum(len(lv.items_down) + len(lv.items_up) for lv in levels)
-    arena = torch.zeros(6 * n_items + 4 * len(levels) + 8, B, G, 2, dtype=torch.float64, device=dev)
+    arena = torch.zeros(7 * n_items + 4 * len(levels) + 8, B, G, 2, dtype=torch.float64, device=dev)
     slot = [0]
 
     def new_stats():
@@ -242,7 +249,8 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         return y2, bwd
 
     # ---- one chain of [ResnetItem, ModulationItem, AttentionItem?, CrossAttentionItem?]
-    def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], items_m, lv: LevelParams, Tl: int):
+    def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], items_m, lv: LevelParams, Tl: int,
+                  li: int = 0):
         C = lv.ch
         narrow = C == 8
         bwds: List = []
@@ -250,12 +258,12 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             r_ = im.resnet
             ss = ss_all[:, ip["ss_off"]:]
             dss = dss_all[:, ip["ss_off"]:]
-            has_att, has_cross = im.attention is not None, im.cross is not None
+            has_att, has_cross, has_inj = im.attention is not None, im.cross is not None, im.inject is not None
             h_stats = new_stats()
-            y_stats = None if (has_att or has_cross) else new_stats()
+            y_stats = None if (has_att or has_cross or has_inj) else new_stats()
             S1, S2 = new_stats(), new_stats()
             h, rr, y = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
-            xn_first = act(B, Tl, C) if (has_att or has_cross) else None
+            xn_first = act(B, Tl, C) if ((has_att or has_cross) and not has_inj) else None
             dgn1 = (grad_for(r_.gn1.weight), grad_for(r_.gn1.bias))
             dgn2 = (grad_for(r_.gn2.weight), grad_for(r_.gn2.bias))
             db1, db2 = grad_for(r_.conv1.bias), grad_for(r_.conv2.bias)
@@ -319,6 +327,39 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             chain = [bwd]
             x, x_stats = y, y_stats
             xn = xn_first
+            if has_inj:
+                # a_unet InjectChannelsItem: conv1x1(cat([x, ctx])) + x, W = [W_x | W_c]
+                jp, conv = ip["inj"], im.inject
+                ctxb, dctxb = plan.ctx[li], plan.dctx[li]
+                n_ctx, ctx_pad = conv.weight.shape[1] - C, ctxb.shape[-1]
+                tmp, yi, dyi = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
+                inj_stats = None if (has_att or has_cross) else new_stats()
+                plan.fwd.append(lambda ctxb=ctxb, jp=jp, tmp=tmp, x=x: ops.conv_gemm(
+                    ctxb, jp["w_c"], tmp, c_in=ctxb.shape[-1], n_valid=C, bias=jp["b"], residual=x))
+                plan.fwd.append(lambda x=x, jp=jp, tmp=tmp, yi=yi, st=inj_stats: ops.conv_gemm(
+                    x, jp["w_x"], yi, c_in=C, n_valid=C, residual=tmp, stats=st, groups=G))
+                gw_inj = grad_for(conv.weight, (C, C + n_ctx, 1)).view(C, C + n_ctx)
+                db_inj = grad_for(conv.bias)
+                wd_x = packed_dgrad(lambda conv=conv, C=C: ops.pack_linear(
+                    conv.weight.detach()[:, :C, 0].t().contiguous()))
+
+                def make_wd_c(conv=conv, C=C, ctx_pad=ctx_pad, n_ctx=n_ctx):
+                    w = torch.zeros(ctx_pad, C, device=dev)
+                    w[:n_ctx] = conv.weight.detach().float()[:, C:, 0].t()
+                    return ops.pack_linear(w)
+                wd_c = packed_dgrad(make_wd_c)
+
+                def inj_bwd(d_out, x=x, ctxb=ctxb, dctxb=dctxb, gw_inj=gw_inj, db_inj=db_inj, wd_x=wd_x,
+                            wd_c=wd_c, dyi=dyi, C=C, n_ctx=n_ctx, ctx_pad=ctx_pad):
+                    ops.colsum(d_out, db_inj)
+                    ops.wgrad(d_out, x, gw_inj[:, :C], n=C, k=C)
+                    ops.wgrad(d_out, ctxb, gw_inj[:, C:], n=C, k=n_ctx)
+                    # d context, summed over the items of this depth (in place through the residual)
+                    ops.conv_gemm(d_out, wd_c, dctxb, c_in=C, n_valid=ctx_pad, residual=dctxb)
+                    ops.conv_gemm(d_out, wd_x, dyi, c_in=C, n_valid=C, residual=d_out)   # + the identity path
+                    return dyi
+                chain.append(inj_bwd)
+                x, x_stats = yi, inj_stats
             for kind, am in (("att", im.attention), ("cross", im.cross)):
                 if am is None:
                     continue
@@ -363,14 +404,14 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                 lv.down.weight.detach().permute(0, 2, 1).reshape(C, kdim).t().contiguous()))
             # [co][tap][ci] (the [B, T/f, f*C] view) -> PyTorch [co][ci][tap]
             gw_down = grad_for(lv.down.weight, (C, lv.factor, lv.in_ch), (0, 2, 1)).view(C, kdim)
-        x, st, items_down_bwd = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl)
+        x, st, items_down_bwd = run_items(x0, st0, Lp["items_down"], lv.items_down, lv, Tl, li=i)
         cur["down_end"] = cursor[0]
         inner = None
         skip = x
         if not innermost:
             x, st, inner = level(i + 1, skip, Tl)
         cur["inner_end"] = cursor[0]
-        x, st, items_up_bwd = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl)
+        x, st, items_up_bwd = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl, li=i)
         gate = ss_all[:, Lp["gate_off"]:]
         dgate = dss_all[:, Lp["gate_off"]:]
         grads[id(lv.merge.weight)] = ("cond_w", Lp["gate_off"], lv.out_ch)
@@ -503,6 +544,8 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         flat.zero_()
         if den is not None:
             den.zero_()
+        for d_ in plan.dctx.values():
+            d_.zero_()
         backward0()
         if den is not None:      # d embedding = LayerNorm backward of the summed context gradients
             ops.ln_film_bwd(den, plan.embedding, None, 0, plan.demb, eps=net.ATT_LN_EPS)
@@ -633,7 +676,9 @@ class _UNetFn(torch.autograd.Function):
     parameter."""
 
     @staticmethod
-    def forward(ctx, net: B200UNet, mode: str, x, noise, sigmas, append, cond, embedding, *params):
+    def forward(ctx, net: B200UNet, mode: str, x, noise, sigmas, append, cond, embedding, ctx_depths,
+                *rest):
+        context, params = rest[:len(ctx_depths)], rest[len(ctx_depths):]
         B, _, T = x.shape
         M = embedding.shape[1] if (embedding is not None and any(net.cross_attentions)) else 0
         need = ctx.needs_input_grad       # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
@@ -659,11 +704,15 @@ class _UNetFn(torch.autograd.Function):
             plan.beta.copy_(torch.sin(angle))
         if M:
             plan.embedding.copy_(embedding)
+        for d_, c_ in zip(ctx_depths, context):      # [B, ctx, T_d] -> channels-last bf16
+            plan.ctx[d_][:, :, : c_.shape[1]].copy_(c_.transpose(1, 2))
         plan.cond.copy_(cond)
         _run(plan, "f", net.use_cuda_graph)
         plan.generation += 1
         ctx.plan, ctx.net, ctx.mode, ctx.generation = plan, net, mode, plan.generation
         ctx.params = params
+        ctx.ctx_depths = ctx_depths
+        ctx.ctx_channels = [c_.shape[1] for c_ in context]
         ctx.has_emb = M > 0
         ctx.x_dtype = x.dtype
         if mode == "loss":
@@ -709,7 +758,7 @@ class _UNetFn(torch.autograd.Function):
                     g = g.reshape(p.shape).clone()       # computed by a `final` (upsample conv folds)
             out.append(None if g is None else (g if g.dtype == p.dtype else g.to(p.dtype)))
         dx = d_append = d_emb = None
-        need = ctx.needs_input_grad        # (net, mode, x, noise, sigmas, append, cond, embedding, ...)
+        need = ctx.needs_input_grad        # (net, mode, x, noise, sigmas, append, cond, embedding, depths, ...)
         if plan.dxin is not None:
             cx = net.x_channels
             if need[2]:
@@ -722,7 +771,9 @@ class _UNetFn(torch.autograd.Function):
                 d_append = plan.dxin[:, cx:].clone()
         if ctx.has_emb and need[7]:
             d_emb = plan.demb.float()
-        return (None, None, dx, None, None, d_append, plan.dcond.clone(), d_emb, *out)
+        d_ctx = [plan.dctx[d_][:, :, :n_].transpose(1, 2).float() if need[9 + j] else None
+                 for j, (d_, n_) in enumerate(zip(ctx.ctx_depths, ctx.ctx_channels))]
+        return (None, None, dx, None, None, d_append, plan.dcond.clone(), d_emb, None, *d_ctx, *out)
 
 
 def _time_cond(net: B200UNet, sigmas: Optional[Tensor], features: Optional[Tensor]) -> Tensor:
@@ -762,6 +813,19 @@ def _train_embedding(net: B200UNet, B: int, embedding: Optional[Tensor],
     return None, None
 
 
+def _context(net: B200UNet, channels):
+    """(depths, tensors) of the InjectChannelsItem contexts, validated like a_unet does."""
+    depths = tuple(i for i, c in enumerate(net.context_channels) if c > 0)
+    tensors = []
+    for d in depths:
+        assert channels is not None and len(channels) > d and channels[d] is not None, \
+            f"context `channels[{d}]` is required (context_channels[{d}] > 0)"
+        assert channels[d].shape[1] == net.context_channels[d], \
+            "context `channels` at depth must match resolution and context_channels"
+        tensors.append(channels[d])
+    return depths, tensors
+
+
 def _net_params(net: B200UNet):
     time_ids = {id(p) for p in (net.time.parameters() if net.time is not None else [])}
     fixed_ids = {id(p) for p in (net.fixed_embedding.parameters() if net.fixed_embedding is not None else [])}
@@ -774,7 +838,6 @@ def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
                  embedding_mask_proba: float = 0.0, channels=None) -> Tensor:
     """mse(net(alpha*x + beta*noise, sigma), alpha*noise - beta*x)  (reference diffusion.py:90-95)."""
     assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
-    assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
     if net.use_embedding_cfg and embedding_scale != 1.0:
         # guidance inside the training objective = two differentiable evaluations (a_unet CFG
         # plugin); no fused-loss form: take the generic route
@@ -783,27 +846,30 @@ def fused_v_loss(net: B200UNet, x: Tensor, noise: Tensor, sigmas: Tensor, *,
         v = differentiable_forward(net, alphas * x + betas * noise, sigmas, features=features,
                                    embedding=embedding, embedding_scale=embedding_scale,
                                    embedding_mask_proba=embedding_mask_proba,
-                                   append_channels=append_channels)
+                                   append_channels=append_channels, channels=channels)
         return F.mse_loss(v, alphas * noise - betas * x)
     cond = _time_cond(net, sigmas, features)
     emb, _ = _train_embedding(net, x.shape[0], embedding, embedding_mask_proba)
-    return _UNetFn.apply(net, "loss", x.float(), noise.float(), sigmas, append_channels, cond, emb,
-                         *_net_params(net))
+    depths, context = _context(net, channels)
+    return _UNetFn.apply(net, "loss", x.float(), noise.float(), sigmas, append_channels, cond, emb, depths,
+                         *context, *_net_params(net))
 
 
 def differentiable_forward(net: B200UNet, x: Tensor, time: Optional[Tensor], *,
                            features: Optional[Tensor] = None, embedding: Optional[Tensor] = None,
                            embedding_scale: float = 1.0, embedding_mask_proba: float = 0.0,
-                           append_channels: Optional[Tensor] = None) -> Tensor:
+                           append_channels: Optional[Tensor] = None, channels=None) -> Tensor:
     """v = net(x, time, ...) with autograd support (custom loss_fn / diffusion_t)."""
     assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
     cond = _time_cond(net, time, features)
     emb, fixed = _train_embedding(net, x.shape[0], embedding, embedding_mask_proba)
     params = _net_params(net)
-    v = _UNetFn.apply(net, "v", x.float(), None, time, append_channels, cond, emb, *params)
+    depths, context = _context(net, channels)
+    v = _UNetFn.apply(net, "v", x.float(), None, time, append_channels, cond, emb, depths, *context, *params)
     if net.use_embedding_cfg and embedding_scale != 1.0:
         # a_unet ClassifierFreeGuidancePlugin: out_masked + (out - out_masked) * scale, both passes
         # differentiable (a second plan of the same shape keeps the first one's activations alive)
-        v_m = _UNetFn.apply(net, "v1", x.float(), None, time, append_channels, cond, fixed, *params)
+        v_m = _UNetFn.apply(net, "v1", x.float(), None, time, append_channels, cond, fixed, depths, *context,
+                            *params)
         v = v_m + (v - v_m) * embedding_scale
     return v.to(x.dtype)

@@ -66,14 +66,17 @@ class AttentionParams(nn.Module):
 
 
 class ItemParams(nn.Module):
-    """One repetition of [ResnetItem, ModulationItem, AttentionItem?, CrossAttentionItem?]."""
+    """One repetition of [ResnetItem, ModulationItem, InjectChannelsItem?, AttentionItem?,
+    CrossAttentionItem?] (reference components.py:89-95)."""
 
     def __init__(self, channels: int, groups: int, features: int, att: bool, cross: bool,
                  head_features: Optional[int], heads: Optional[int],
-                 embedding_features: Optional[int]):
+                 embedding_features: Optional[int], context: int = 0):
         super().__init__()
         self.resnet = ResnetParams(channels, groups)
         self.modulation = ModulationParams(channels, features)
+        # a_unet InjectChannelsItem: Conv1d(C + ctx -> C, k=1) over cat([x, channels[depth]]), + x
+        self.inject = nn.Conv1d(channels + context, channels, 1) if context > 0 else None
         self.attention = AttentionParams(channels, head_features, heads) if att else None
         self.cross = (AttentionParams(channels, head_features, heads, embedding_features)
                       if cross else None)
@@ -186,8 +189,8 @@ class B200UNet(nn.Module):
                 "precomputed `embedding=` with use_text_conditioning=False (SURVEY.md 3.4)")
         if not use_modulation:
             raise NotImplementedError("use_modulation=False (SkipCat) is outside the B200 hot path")
-        if any(c > 0 for c in context_channels):
-            raise NotImplementedError("context_channels / InjectChannelsItem is outside the hot path")
+        for c, ctx in zip(channels, context_channels):
+            assert ctx == 0 or c >= 16, "InjectChannelsItem is built for levels with >= 16 channels"
         if any(attentions) or any(cross_attentions):
             assert exists(attention_features) and exists(attention_heads), \
                 "AttentionItem requires attention_features and attention_heads"
@@ -200,6 +203,7 @@ class B200UNet(nn.Module):
         self.in_channels, self.out_channels = in_channels, default(out_channels, in_channels)
         self.channels, self.factors, self.items = list(channels), list(factors), list(items)
         self.attentions, self.cross_attentions = list(attentions), list(cross_attentions)
+        self.context_channels = list(context_channels)
         self.groups, self.features = resnet_groups, modulation_features
         self.heads, self.head_features = attention_heads, attention_features
         self.embedding_features = embedding_features
@@ -222,7 +226,7 @@ class B200UNet(nn.Module):
                                groups=resnet_groups, features=modulation_features,
                                att=bool(attentions[i]), cross=bool(cross_attentions[i]),
                                head_features=attention_features, heads=attention_heads,
-                               embedding_features=embedding_features)
+                               embedding_features=embedding_features, context=context_channels[i])
 
         self.net = build(0)
         self._plans: Dict[Tuple, _Plan] = {}
@@ -390,6 +394,14 @@ class B200UNet(nn.Module):
                 if r.conv1.weight.shape[0] in (32, 64):    # thin levels: fused ConvBlock kernel
                     d["w1_raw"], d["w2_raw"] = f32(r.conv1.weight), f32(r.conv2.weight)
                     d["w1_mid"], d["w2_mid"] = ops.pack_mid_conv(r.conv1.weight), ops.pack_mid_conv(r.conv2.weight)
+            if it.inject is not None:
+                C_ = it.inject.weight.shape[0]
+                wi = it.inject.weight.detach().float()[:, :, 0]
+                ctx = wi.shape[1] - C_
+                wc = torch.zeros(C_, ops.round_up(ctx, 16), device=wi.device)
+                wc[:, :ctx] = wi[:, C_:]
+                d["inj"] = {"w_x": ops.pack_linear(wi[:, :C_]), "w_c": ops.pack_linear(wc),
+                            "b": f32(it.inject.bias)}
             if it.attention is not None:
                 d["att"] = pack_att(it.attention, True)
             if it.cross is not None:
@@ -511,12 +523,15 @@ class B200UNet(nn.Module):
         plan.embedding = torch.zeros(Bh, M, self.embedding_features, dtype=torch.bfloat16,
                                      device=dev) if M else None
         plan.cfg_scale = None
+        plan.ctx = {i: torch.zeros(Bh, (T // _prod(self.factors[:i + 1])), ops.round_up(c, 16),
+                                   dtype=torch.bfloat16, device=dev)
+                    for i, c in enumerate(self.context_channels) if c > 0}
         plan.en = None                       # LayerNorm(embedding), shared by all cross-attentions
         plan.pre = []                        # step-invariant launches of a sampling plan
         add_ctx = plan.pre.append if mode == "sample" else plan.add
 
         # ---- statistics arena (zeroed once per forward)
-        n_slots = 2 + sum(2 * (len(lv.items_down) + len(lv.items_up)) + 3 for lv in levels)
+        n_slots = 2 + sum(3 * (len(lv.items_down) + len(lv.items_up)) + 3 for lv in levels)
         arena = torch.zeros(n_slots, Bh, G, 2, dtype=torch.float64, device=dev)
         slot_i = [0]
 
@@ -549,7 +564,7 @@ class B200UNet(nn.Module):
 
         # ---- one item chain
         def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], lv: LevelParams, Tl: int,
-                      last_needs_stats: bool) -> Tuple[Tensor, Optional[Tensor]]:
+                      last_needs_stats: bool, li: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
             C = lv.ch
             narrow = C == 8
             # thin levels (C = 32, 64) are HBM-bound: one fused ConvBlock kernel (mid_conv.cu)
@@ -557,10 +572,10 @@ class B200UNet(nn.Module):
             thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 4 == 0)
             for idx, ip in enumerate(items_p):
                 ss = ss_all[:, ip["ss_off"]:]
-                has_att, has_cross = "att" in ip, "cross" in ip
+                has_att, has_cross, has_inj = "att" in ip, "cross" in ip, "inj" in ip
                 item_last = idx == len(items_p) - 1
                 want_stats = (not item_last) or last_needs_stats
-                mod_stats = new_stats() if (want_stats and not (has_att or has_cross)) else None
+                mod_stats = new_stats() if (want_stats and not (has_att or has_cross or has_inj)) else None
                 h_stats = new_stats()
                 if thin:
                     h = pool.get(Bh, Tl, C)
@@ -599,7 +614,7 @@ class B200UNet(nn.Module):
                         plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
                             a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
                         pool.put(a)
-                    xn_first = pool.get(Bh, Tl, C) if (has_att or has_cross) else None
+                    xn_first = pool.get(Bh, Tl, C) if ((has_att or has_cross) and not has_inj) else None
                     # Modulation and the following attention pre-norm in ONE pass over the rows
                     plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats, xn=xn_first: ops.ln_film(
                         r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS, y2=xn, eps2=self.ATT_LN_EPS))
@@ -608,6 +623,20 @@ class B200UNet(nn.Module):
                 # the item's input is dead now (a level's skip is the chain's *output*)
                 pool.put(x)
                 x, x_stats = y, mod_stats
+                if has_inj:
+                    # InjectChannelsItem: conv1x1(cat([x, ctx])) + x as two accumulating GEMMs
+                    # (W = [W_x | W_c]): tmp = ctx W_c^T + b + x ; out = x W_x^T + tmp
+                    jp = ip["inj"]
+                    ctxb = plan.ctx[li]
+                    tmp, out_i = pool.get(Bh, Tl, C), pool.get(Bh, Tl, C)
+                    inj_stats = new_stats() if (want_stats and not (has_att or has_cross)) else None
+                    plan.add(lambda ctxb=ctxb, jp=jp, tmp=tmp, x=x: ops.conv_gemm(
+                        ctxb, jp["w_c"], tmp, c_in=ctxb.shape[-1], n_valid=C, bias=jp["b"], residual=x))
+                    plan.add(lambda x=x, jp=jp, tmp=tmp, o=out_i, st=inj_stats: ops.conv_gemm(
+                        x, jp["w_x"], o, c_in=C, n_valid=C, residual=tmp, stats=st, groups=G))
+                    pool.put(tmp)
+                    pool.put(x)
+                    x, x_stats = out_i, inj_stats
                 mid = (self.heads or 0) * 64
                 for kind in ("att", "cross"):
                     if kind not in ip:
@@ -674,12 +703,12 @@ class B200UNet(nn.Module):
                 plan.add(lambda x=x, st=st: ops.conv_gemm(
                     x_in.view(Bh, Tl, lv.factor * lv.in_ch), Lp["down_w"], x, c_in=lv.factor * lv.in_ch,
                     n_valid=C, bias=Lp["down_b"], stats=st, groups=G))
-            x, st = run_items(x, st, Lp["items_down"], lv, Tl, last_needs_stats=innermost)
+            x, st = run_items(x, st, Lp["items_down"], lv, Tl, last_needs_stats=innermost, li=i)
             if not innermost:
                 skip = x
                 x, st = run_level(i + 1, skip, Tl)
                 pool.put(skip)
-            x, st = run_items(x, st, Lp["items_up"], lv, Tl, last_needs_stats=False)
+            x, st = run_items(x, st, Lp["items_up"], lv, Tl, last_needs_stats=False, li=i)
             gate = ss_all[:, Lp["gate_off"]:]
             if i == 0:
                 plan.h0 = x
@@ -804,10 +833,20 @@ class B200UNet(nn.Module):
         plan.step.zero_()
 
     def _stage_inputs(self, plan: _Plan, x: Tensor, time: Optional[Tensor], features, embedding,
-                      embedding_scale: float, embedding_mask_proba: float, append_channels):
+                      embedding_scale: float, embedding_mask_proba: float, append_channels,
+                      channels=None):
         B = x.shape[0]
         Bh = plan.sigma.shape[0]
         cfg = Bh == 2 * B
+        for d, buf in plan.ctx.items():       # InjectChannelsItem context: [B, ctx, T_d] -> channels-last bf16
+            assert channels is not None and channels[d] is not None, \
+                f"context `channels[{d}]` is required (context_channels[{d}] > 0)"
+            c = channels[d]
+            assert c.shape[1] == self.context_channels[d] and c.shape[2] == buf.shape[1], \
+                "context `channels` at depth must match resolution and context_channels"
+            buf[:B, :, : c.shape[1]].copy_(c.transpose(1, 2))
+            if cfg:
+                buf[B:, :, : c.shape[1]].copy_(c.transpose(1, 2))
         if plan.x.data_ptr() != x.data_ptr():
             plan.x.copy_(x)
         if self.append_channels:
@@ -850,30 +889,30 @@ class B200UNet(nn.Module):
                 embedding_mask_proba: float = 0.0, channels=None,
                 append_channels: Optional[Tensor] = None) -> Tensor:
         assert x.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
-        assert channels is None, "context `channels` (InjectChannelsItem) is outside the hot path"
         if self.use_embedding_cfg:
             assert exists(embedding), "ClassiferFreeGuidancePlugin requires embedding"
+        ctx_list = [c for c in (channels or []) if exists(c)]
         if torch.is_grad_enabled() and (
                 any(p.requires_grad for p in self.parameters()) or
-                any(exists(t) and t.requires_grad for t in (x, features, embedding, append_channels))):
+                any(exists(t) and t.requires_grad for t in (x, features, embedding, append_channels, *ctx_list))):
             # differentiable: custom loss_fn / diffusion_t (reference models.py:28,37)
             from .training import differentiable_forward
             return differentiable_forward(self, x, time, features=features, embedding=embedding,
                                           embedding_scale=embedding_scale,
                                           embedding_mask_proba=embedding_mask_proba,
-                                          append_channels=append_channels)
+                                          append_channels=append_channels, channels=channels)
         return self._forward_inference(x, time, features, embedding, embedding_scale,
-                                       embedding_mask_proba, append_channels)
+                                       embedding_mask_proba, append_channels, channels)
 
     @torch.no_grad()
     def _forward_inference(self, x, time, features, embedding, embedding_scale,
-                           embedding_mask_proba, append_channels) -> Tensor:
+                           embedding_mask_proba, append_channels, channels=None) -> Tensor:
         self._check_untracked_updates()
         B, T, Bh, M = self._shape_key(x, embedding, embedding_scale)
         plan = self._plan(B, T, Bh, M, "v", (float(embedding_scale) if Bh != B else None,
                                              exists(features)))
         self._stage_inputs(plan, x.float(), time, features, embedding, embedding_scale,
-                           embedding_mask_proba, append_channels)
+                           embedding_mask_proba, append_channels, channels)
         self._execute(plan)
         return plan.v.clone().to(x.dtype)
 
@@ -890,7 +929,8 @@ class B200UNet(nn.Module):
         plan = self._plan(B, T, Bh, M, "sample", (float(scale) if Bh != B else None,
                                                   exists(kwargs.get("features"))))
         self._stage_inputs(plan, x_noisy.float(), sigmas[0], kwargs.get("features"), embedding, scale,
-                           kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"))
+                           kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"),
+                           kwargs.get("channels"))
         for fn in plan.pre:          # cross-attention context K/V: once per call
             fn()
         num_steps = sigmas.shape[0] - 1
@@ -932,7 +972,8 @@ def _inpaint_loop(self, x_noisy: Tensor, source: Tensor, mask: Tensor, sigmas: T
     plan = self._plan(B, T, Bh, M, "sample", (float(scale) if Bh != B else None,
                                               exists(kwargs.get("features"))))
     self._stage_inputs(plan, x_noisy.float(), sigmas[0], kwargs.get("features"), embedding, scale,
-                       kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"))
+                       kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"),
+                       kwargs.get("channels"))
     for fn in plan.pre:
         fn()
     num_steps = sigmas.shape[0] - 1
@@ -980,6 +1021,13 @@ def _copy_tree(dst, src) -> None:
     elif isinstance(dst, (list, tuple)):
         for d, s_ in zip(dst, src):
             _copy_tree(d, s_)
+
+
+def _prod(vals) -> int:
+    out = 1
+    for v in vals:
+        out *= v
+    return out
 
 
 def _pad_to(t: Tensor, n: int) -> Tensor:

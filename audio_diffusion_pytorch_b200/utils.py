@@ -25,6 +25,12 @@ def default(val: Any, fallback: Union[Any, Callable[[], Any]]) -> Any:
     return fallback() if inspect.isfunction(fallback) else fallback
 
 
+def closest_power_2(x: float) -> int:
+    """The power of two nearest to x (reference utils.py:45-49; DiffusionAE.decode sizes its noise with it)."""
+    lo = 2 ** int(math.floor(math.log2(x)))
+    return lo if x - lo <= 2 * lo - x else 2 * lo
+
+
 def groupby(prefix: str, d: Dict[str, Any], keep_prefix: bool = False) -> Tuple[Dict, Dict]:
     """Partition keyword arguments: ({keys that start with `prefix`, prefix removed unless
     keep_prefix}, {all others}) — how `diffusion_*`, `sampler_*` and `mel_*` options reach their

@@ -140,11 +140,45 @@ def case_tiny_inpaint():
                         param_fingerprint=fingerprint(m_port))
 
 
+def case_tiny_autoencoder():
+    """DiffusionAE (models.py:70-131) with a toy encoder: latent [B,16,T/16] injected at depth 2
+    (InjectChannelsItem at the C = 64 level, followed by attention)."""
+    cfg = dict(TINY, inject_depth=2)
+    torch.manual_seed(0)
+    m_ref = ref.DiffusionAE(encoder=port.ToyEncoder(), net_t=ref.UNetV0, diffusion_t=ref.VDiffusion,
+                            sampler_t=ref.VSampler, **cfg)
+    torch.manual_seed(0)
+    m_port = port.DiffusionAEPort(encoder=port.ToyEncoder(), **cfg)
+    same(torch.cat([p.flatten() for p in m_ref.parameters()]),
+         torch.cat([p.flatten() for p in m_port.parameters()]), "same-seed construction")
+    g = torch.Generator().manual_seed(24)
+    audio = torch.randn(2, 2, 4096, generator=g)
+    torch.manual_seed(7)
+    l_ref = m_ref(audio)
+    l_ref.backward()
+    torch.manual_seed(7)
+    l_port = m_port(audio)
+    l_port.backward()
+    same(l_port.detach(), l_ref.detach(), "DiffusionAE.forward loss")
+    for (n, p), q in zip(m_ref.named_parameters(), m_port.parameters()):
+        assert torch.equal(p.grad, q.grad), n
+    print("  port == reference (bit-exact): every parameter gradient (encoder included)")
+    latent = m_ref.encode(audio).detach()
+    d_ref = m_ref.decode(latent, num_steps=3, generator=torch.Generator().manual_seed(9))
+    d_port = m_port.decode(latent, num_steps=3, generator=torch.Generator().manual_seed(9))
+    same(d_port, d_ref, "DiffusionAE.decode 3 steps")
+    np.savez_compressed(os.path.join(OUT, "tiny_autoencoder.npz"), audio_seed=24, loss_seed=7,
+                        loss=l_ref.detach().numpy(), decode3=d_ref.numpy(), decode_seed=9,
+                        enc_grad=m_ref.encoder.conv.weight.grad.numpy(),
+                        param_fingerprint=fingerprint(m_port))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for case in (case_tiny_50_steps, case_tiny_inpaint, case_cfg3_readme_scale, case_readme_full_size):
+    for case in (case_tiny_50_steps, case_tiny_inpaint, case_tiny_autoencoder, case_cfg3_readme_scale,
+                 case_readme_full_size):
         if only and case.__name__ not in only:
             continue
         print(case.__name__)

@@ -243,6 +243,54 @@ class DiffusionModelPort(nn.Module):
         return self.sampler(*args, **kwargs)
 
 
+class DiffusionAEPort(DiffusionModelPort):
+    """models.py:70-131 (DiffusionAE): latent injected at `inject_depth` (InjectChannelsItem)."""
+
+    def __init__(self, in_channels: int, channels: Sequence[int], encoder: nn.Module,
+                 inject_depth: int, latent_factor: Optional[int] = None, adapter=None, **kwargs):
+        context_channels = [0] * len(channels)
+        context_channels[inject_depth] = encoder.out_channels                        # :84-85
+        super().__init__(in_channels=in_channels, channels=channels,
+                         context_channels=context_channels, **kwargs)
+        self.in_channels, self.encoder, self.inject_depth = in_channels, encoder, inject_depth
+        self.latent_factor = a_unet.default(latent_factor, encoder.downsample_factor)   # :96
+        self.adapter = adapter.requires_grad_(False) if adapter is not None else None
+
+    def forward(self, x: Tensor, with_info: bool = False, **kwargs):                # :99-110
+        latent, info = self.encoder(x, with_info=True)
+        channels = [None] * self.inject_depth + [latent]
+        x = self.adapter.encode(x) if self.adapter is not None else x
+        loss = super().forward(x, channels=channels, **kwargs)
+        return (loss, info) if with_info else loss
+
+    @torch.no_grad()
+    def decode(self, latent: Tensor, generator: Optional[Generator] = None, **kwargs) -> Tensor:
+        b = latent.shape[0]                                                          # :116-131
+        exponent = math.log2(latent.shape[2] * self.latent_factor)
+        lo, hi = math.floor(exponent), math.ceil(exponent)
+        target = latent.shape[2] * self.latent_factor
+        length = 2 ** int(min((lo, hi), key=lambda z: abs(target - 2 ** z)))         # utils.py:45-49
+        noise = torch.randn((b, self.in_channels, length), device=latent.device,
+                            dtype=latent.dtype, generator=generator)
+        channels = [None] * self.inject_depth + [latent]
+        out = super().sample(noise, channels=channels, **kwargs)
+        return self.adapter.decode(out) if self.adapter is not None else out
+
+
+class ToyEncoder(nn.Module):
+    """Test fixture: a minimal encoder with the interface DiffusionAE needs (`out_channels`,
+    `downsample_factor`, `forward(x, with_info)`); stands in for audio_encoders_pytorch.MelE1d."""
+
+    def __init__(self, in_channels: int = 2, out_channels: int = 16, downsample_factor: int = 16):
+        super().__init__()
+        self.out_channels, self.downsample_factor = out_channels, downsample_factor
+        self.conv = nn.Conv1d(in_channels, out_channels, downsample_factor, stride=downsample_factor)
+
+    def forward(self, x: Tensor, with_info: bool = False):
+        z = torch.tanh(self.conv(x))
+        return (z, {"latent": z}) if with_info else z
+
+
 class DiffusionUpsamplerPort(DiffusionModelPort):
     """models.py:134-165 (DiffusionUpsampler)."""
 

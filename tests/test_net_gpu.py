@@ -311,3 +311,28 @@ def test_vinpainter_vs_golden(adp, oracle_port, golden_dir, monkeypatch):
     assert e <= 5e-3
     # the last step ends at sigma = 0: alpha = 1, beta = 0 -> the known region IS the source
     assert rel_l2(out.cpu()[mask], source[mask]) <= 1e-5
+
+
+def test_autoencoder_decode_vs_golden(adp, oracle_port, golden_dir):
+    """DiffusionAE (reference models.py:70-131): the latent of a (toy) encoder injected at depth 2
+    by InjectChannelsItem (conv1x1 over cat([x, latent]) + x, here followed by attention);
+    decode = 3-step VSampler conditioned on the latent, against the unmodified reference."""
+    g = load(golden_dir, "tiny_autoencoder.npz")
+    cfg = dict(TINY, inject_depth=2)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionAEPort(encoder=oracle_port.ToyEncoder(), **cfg)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    torch.manual_seed(0)
+    model = adp.DiffusionAE(encoder=oracle_port.ToyEncoder(), net_t=adp.UNetV0, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.encoder.load_state_dict(ref.encoder.state_dict())
+    audio = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["audio_seed"])))
+    latent = model.encode(audio.to(DEV))
+    assert rel_l2(latent, ref.encode(audio) if hasattr(ref, "encode") else ref.encoder(audio)) < 1e-5
+    # the reference draws decode()'s noise on latent.device: feed the CPU draw of the golden run
+    noise = torch.randn((2, 2, 4096), generator=torch.Generator().manual_seed(int(g["decode_seed"])))
+    out = model.sampler(noise.to(DEV), num_steps=3, channels=[None, None, latent])
+    e = rel_l2(out, torch.from_numpy(g["decode3"]))
+    print(f"DiffusionAE decode (3 steps, latent injected at depth 2): rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    assert model.decode(latent, num_steps=2).shape == (2, 2, 4096)      # closest_power_2(256 * 16)

@@ -172,3 +172,20 @@ def test_oracle_readme_scale_goldens(oracle_port, golden_dir):
     with torch.no_grad():
         v5 = m.net(x, t(g["sigma"]), embedding=emb, embedding_scale=5.0)
     assert rel_l2(v5, t(g["v_scale5"])) <= RTOL
+
+
+def test_oracle_autoencoder(oracle_port, golden_dir):
+    """tiny_autoencoder.npz: DiffusionAE loss, encoder gradient and 3-step decode."""
+    g = load(golden_dir, "tiny_autoencoder.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionAEPort(encoder=oracle_port.ToyEncoder(), **dict(TINY, inject_depth=2))
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    audio = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["audio_seed"])))
+    torch.manual_seed(int(g["loss_seed"]))
+    loss = m(audio)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(m.encoder.conv.weight.grad, t(g["enc_grad"])) <= 10 * RTOL
+    latent = m.encoder(audio).detach()
+    out = m.decode(latent, num_steps=3, generator=torch.Generator().manual_seed(int(g["decode_seed"])))
+    assert rel_l2(out, t(g["decode3"])) <= 10 * RTOL

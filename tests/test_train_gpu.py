@@ -367,3 +367,39 @@ def test_guidance_under_autograd(oracle_port):
     got = [q for (n, p), q in zip(ref.net.named_parameters(), model.net.parameters()) if p.grad is not None]
     worst, cos = compare_grads(ref_named, got)
     assert worst < 0.1 and cos > 1 - 2e-3
+
+
+def test_autoencoder_trains_encoder_through_injected_context(oracle_port):
+    """DiffusionAE.forward (reference models.py:99-110): loss parity, U-Net gradients incl. the
+    InjectChannelsItem convs, and the ENCODER's gradient, which only arrives through d(context)."""
+    import audio_diffusion_pytorch_b200 as adp
+    cfg = dict(ATT, inject_depth=2)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionAEPort(encoder=oracle_port.ToyEncoder(), **cfg)
+    torch.manual_seed(0)
+    model = adp.DiffusionAE(encoder=oracle_port.ToyEncoder(), net_t=adp.UNetV0, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.encoder.load_state_dict(ref.encoder.state_dict())
+    g = torch.Generator().manual_seed(24)
+    audio = torch.randn(2, 2, 4096, generator=g)
+    for call in range(3):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(91)
+        loss = model(audio.to(DEV))
+        loss.backward()
+    torch.manual_seed(91)
+    sigma = torch.rand(2, device=DEV).cpu()
+    noise = torch.randn(2, 2, 4096, device=DEV).cpu()
+    latent = ref.encoder(audio)
+    loss_ref = oracle_loss(ref.net, audio, noise, sigma, channels=[None, None, latent])
+    loss_ref.backward()
+    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    print(f"autoencoder loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < GRAD_TOL and cos > 1 - 1e-3
+    got, want = model.encoder.conv.weight.grad, ref.encoder.conv.weight.grad
+    assert got is not None, "the encoder received no gradient"
+    e = float((got.cpu() - want).norm() / want.norm())
+    print(f"encoder conv.weight.grad rel-L2 {e:.3e}")
+    assert e < GRAD_TOL
