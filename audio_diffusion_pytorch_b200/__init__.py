@@ -4,10 +4,10 @@ for the UNetV0 + VDiffusion/VSampler hot path, executed by hand-written sm_100a 
 Out-of-scope names of the reference raise on use instead of silently
 running something else."""
 from .components import AppendChannelsPlugin, MelSpectrogram, UNetV0
-from .diffusion import (Diffusion, Distribution, Inpainter, LinearSchedule, Sampler, Schedule,
-                        UniformDistribution, VDiffusion, VInpainter, VSampler)
-from .models import (AdapterBase, DiffusionAE, DiffusionModel, DiffusionUpsampler, DiffusionVocoder,
-                     EncoderBase)
+from .diffusion import (ARVDiffusion, ARVSampler, Diffusion, Distribution, Inpainter, LinearSchedule,
+                        Sampler, Schedule, UniformDistribution, VDiffusion, VInpainter, VSampler)
+from .models import (AdapterBase, DiffusionAE, DiffusionAR, DiffusionModel, DiffusionUpsampler,
+                     DiffusionVocoder, EncoderBase)
 from .unet import B200UNet
 
 
@@ -22,9 +22,8 @@ def _out_of_scope(name: str, why: str):
 
 XUNet = B200UNet
 LTPlugin = _out_of_scope("LTPlugin", "not used by any model class or config")
-DiffusionAR = _out_of_scope("DiffusionAR", "use_modulation=False / SkipCat path, SURVEY.md 8f item 1")
 
 __all__ = ["UNetV0", "XUNet", "LTPlugin", "MelSpectrogram", "VDiffusion", "VSampler", "VInpainter",
            "LinearSchedule", "UniformDistribution", "Diffusion", "Distribution", "Sampler",
            "Schedule", "DiffusionModel", "DiffusionUpsampler", "DiffusionVocoder", "DiffusionAE",
-           "DiffusionAR", "EncoderBase", "AdapterBase", "AppendChannelsPlugin", "B200UNet", "Inpainter"]
+           "DiffusionAR", "ARVDiffusion", "ARVSampler", "EncoderBase", "AdapterBase", "AppendChannelsPlugin", "B200UNet", "Inpainter"]

@@ -504,6 +504,34 @@ __global__ void inpaint_blend_kernel(float* __restrict__ x, const float* __restr
     if (mask[i]) x[i] = a1 * source[i] + b1 * noise[i];
 }
 
+// ARVSampler step (reference diffusion.py:231-235): every position carries its own noise level.
+// chan fp32 [B, C+1, T] is the net input: channels 0..C-1 = current, channel C = sigma_i.  With
+// a = cos(sigma pi/2), b = sin(sigma pi/2):  x_pred = a_i x - b_i v, n_pred = b_i x + a_i v,
+// current' = a_n x_pred + b_n n_pred; current' and sigma_{i+1} are written back into chan, which
+// is then the next step's net input.  One thread per (batch, position).
+__global__ void arv_step_kernel(float* __restrict__ chan, const float* __restrict__ v,
+                                const float* __restrict__ sig_next, int B, int C, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t n = static_cast<int64_t>(B) * T;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / T);
+    const int t = static_cast<int>(i - static_cast<int64_t>(b) * T);
+    float* cb = chan + static_cast<size_t>(b) * (C + 1) * T + t;
+    const float* vb = v + static_cast<size_t>(b) * C * T + t;
+    const float s0 = cb[static_cast<size_t>(C) * T], s1 = sig_next[i];
+    const float a0 = cospif(0.5f * s0), b0 = sinpif(0.5f * s0);
+    const float a1 = cospif(0.5f * s1), b1 = sinpif(0.5f * s1);
+    for (int c = 0; c < C; ++c) {
+      const float x = cb[static_cast<size_t>(c) * T], vv = vb[static_cast<size_t>(c) * T];
+      const float xp = a0 * x - b0 * vv, np = b0 * x + a0 * vv;
+      cb[static_cast<size_t>(c) * T] = a1 * xp + b1 * np;
+    }
+    cb[static_cast<size_t>(C) * T] = s1;
+  }
+}
+
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                  int64_t n) {
   pdl_launch_dependents();
@@ -675,6 +703,15 @@ extern "C" int adp_inpaint_blend(float* x, const float* source, const float* noi
   ADP_CHECK(x && source && noise && mask && ab && n > 0, "adp_inpaint_blend: bad args");
   ADP_CUDA(launch_k(inpaint_blend_kernel, dim3(pick_grid(static_cast<size_t>(n), 256 * 4, 148 * 8)),
                     dim3(256), (size_t)0, as_stream(stream), x, source, noise, mask, ab, n));
+  ADP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int adp_arv_step(float* chan, const float* v, const float* sig_next, int B, int C, int T,
+                            adp_stream_t stream) {
+  ADP_CHECK(chan && v && sig_next && B > 0 && C > 0 && T > 0, "adp_arv_step: bad args");
+  ADP_CUDA(launch_k(arv_step_kernel, dim3(pick_grid(static_cast<size_t>(B) * T, 256, 148 * 8)), dim3(256),
+                    (size_t)0, as_stream(stream), chan, v, sig_next, B, C, T));
   ADP_LAUNCH_CHECK();
   return 0;
 }

@@ -105,6 +105,119 @@ class VDiffusion(Diffusion):
         return self.loss_fn(v_pred, v_target)                                     # :95
 
 
+class ARVDiffusion(Diffusion):
+    """v-objective with one noise level per SPLIT of the clip (reference diffusion.py:98-130): the
+    per-position sigma rides along as an extra input channel, the net has no time conditioning.
+
+    RNG contract kept: `rand((B, 1, num_splits))` first, then `randn_like(x)`, both on x.device.
+    The pointwise noising runs as tensor ops (autograd records them for dL/dx); the net is the
+    B200 differentiable program (`B200UNet.forward` under grad mode)."""
+
+    def __init__(self, net: nn.Module, length: int, num_splits: int, loss_fn: Any = F.mse_loss):
+        super().__init__()
+        assert length % num_splits == 0, "length must be divisible by num_splits"
+        self.net = net
+        self.length, self.num_splits = length, num_splits
+        self.split_length = length // num_splits
+        self.loss_fn = loss_fn
+
+    def get_alpha_beta(self, sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+        return _alpha_beta(sigmas)
+
+    def forward(self, x: Tensor, **kwargs) -> Tensor:
+        b, t = x.shape[0], x.shape[2]
+        assert t == self.length, "input length must match length"
+        per_split = torch.rand((b, 1, self.num_splits), device=x.device, dtype=x.dtype)      # :118
+        sigmas = per_split.repeat_interleave(self.split_length, dim=2)                      # :119
+        noise = torch.randn_like(x)                                                          # :121
+        alphas, betas = _alpha_beta(sigmas)
+        x_noisy = alphas * x + betas * noise                                                 # :124
+        v_target = alphas * noise - betas * x                                                # :125
+        v_pred = self.net(torch.cat([x_noisy, sigmas], dim=1), **kwargs)                     # :127-129
+        return self.loss_fn(v_pred, v_target)
+
+
+class ARVSampler(Sampler):
+    """Autoregressive sampler over a ladder of per-split noise levels (reference
+    diffusion.py:193-298).  `sample_loop` keeps cat([current, sigma_i]) resident in the net's input
+    buffer: one graph launch + one `adp_arv_step` per step (B200UNet.arv_loop)."""
+
+    def __init__(self, net: nn.Module, in_channels: int, length: int, num_splits: int):
+        super().__init__()
+        assert length % num_splits == 0, "length must be divisible by num_splits"
+        self.length, self.in_channels, self.num_splits = length, in_channels, num_splits
+        self.split_length = length // num_splits
+        self.net = net
+
+    @property
+    def device(self):
+        return next(self.net.parameters()).device
+
+    def get_alpha_beta(self, sigmas: Tensor) -> Tuple[Tensor, Tensor]:
+        return _alpha_beta(sigmas)
+
+    def get_sigmas_ladder(self, num_items: int, num_steps_per_split: int) -> Tensor:
+        """[steps+1, B, 1, 2*(n//2)*l]: the first half of the window stays clean (context), the
+        second half is a staircase of n//2 noise levels, lowest first, that one `sample_loop`
+        lowers by exactly one stair; row `steps` is row 0 shifted by one split (reference :213-221)."""
+        n_half, l, k = self.num_splits // 2, self.split_length, num_steps_per_split
+        levels = torch.linspace(1, 0, k * n_half, device=self.device).view(n_half, k).t()    # [k, n_half]
+        stairs = levels.repeat_interleave(l, dim=1).flip(-1)                                 # [k, n_half*l]
+        stairs = torch.cat([stairs, torch.zeros_like(stairs[:1])], dim=0)
+        stairs[-1, l:] = stairs[0, :-l]
+        ladder = torch.cat([torch.zeros_like(stairs), stairs], dim=-1)
+        return ladder[:, None, None, :].repeat(1, num_items, 1, 1)
+
+    def sample_loop(self, current: Tensor, sigmas: Tensor, show_progress: bool = False, **kwargs) -> Tensor:
+        num_steps = sigmas.shape[0] - 1
+        host_sig = sigmas[:, 0, 0, 0].tolist() if show_progress else None
+        bar = tqdm(range(num_steps), disable=not show_progress)
+
+        def progress():
+            for i in bar:
+                yield i
+                if host_sig is not None:
+                    bar.set_description(f"Sampling (noise={host_sig[i + 1]:.2f})")
+
+        net = _inner_b200(self.net)
+        if net is not None:
+            return net.arv_loop(current, sigmas, progress=progress() if show_progress else None, **kwargs)
+        chan = torch.cat([current, sigmas[0]], dim=1).float().contiguous()
+        sig = sigmas.float().reshape(num_steps + 1, current.shape[0], -1).contiguous()
+        for i in progress():
+            v = self.net(chan, **kwargs).float().contiguous()                                 # :231-232
+            ops.arv_step(chan, v, sig[i + 1])                                                 # :233-235
+        return chan[:, : current.shape[1]].to(current.dtype)
+
+    def sample_start(self, num_items: int, num_steps: int, **kwargs) -> Tensor:
+        b, c, t = num_items, self.in_channels, self.length
+        sigmas = torch.linspace(1, 0, num_steps + 1, device=self.device)                      # :243
+        sigmas = sigmas[:, None, None, None].repeat(1, b, 1, t)
+        noise = torch.randn((b, c, t), device=self.device) * sigmas[0]                        # :245
+        return self.sample_loop(current=noise, sigmas=sigmas, **kwargs)
+
+    @torch.no_grad()
+    def forward(self, num_items: int, num_chunks: int, num_steps: int, start: Optional[Tensor] = None,
+                show_progress: bool = False, **kwargs) -> Tensor:
+        n = self.num_splits
+        assert num_chunks >= n, f"required at least {n} chunks"
+        start = self.sample_start(num_items=num_items, num_steps=num_steps, **kwargs)         # :263
+        if num_chunks == n:
+            return start
+        assert num_steps >= n, "num_steps must be greater than num_splits"
+        sigmas = self.get_sigmas_ladder(num_items=num_items, num_steps_per_split=num_steps // n)
+        alphas, betas = _alpha_beta(sigmas)
+        # noise the start window up to the ladder, then slide: every pass lowers the last n chunks
+        # by one stair and a fresh pure-noise chunk enters at the end (:278-296)
+        noised = alphas[0] * start + betas[0] * torch.randn_like(start)
+        chunks = list(noised.chunk(chunks=n, dim=-1))
+        for _ in tqdm(range(num_chunks), disable=not show_progress):
+            window = self.sample_loop(current=torch.cat(chunks[-n:], dim=-1), sigmas=sigmas, **kwargs)
+            chunks[-n:] = list(window.chunk(chunks=n, dim=-1))
+            chunks.append(torch.randn((num_items, self.in_channels, self.split_length), device=self.device))
+        return torch.cat(chunks[:num_chunks], dim=-1)
+
+
 class Inpainter(nn.Module):
     pass
 

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import Generator, Tensor, nn
 
 from .components import AppendChannelsPlugin, MelSpectrogram
-from .diffusion import VDiffusion, VSampler
+from .diffusion import ARVDiffusion, ARVSampler, VDiffusion, VSampler
 from .unet import UNetV0
 from .utils import closest_power_2, default, downsample, groupby, randn_like, upsample
 
@@ -98,6 +98,20 @@ class DiffusionAE(DiffusionModel):
         context = [None] * self.inject_depth + [latent]
         out = super().sample(noise, channels=context, **kwargs)
         return self.adapter.decode(out) if self.adapter is not None else out
+
+
+class DiffusionAR(DiffusionModel):
+    """Autoregressive diffusion over a sliding window (reference models.py:227-250): the net sees
+    the waveform plus one channel carrying the per-position noise level, has no time conditioning
+    and no ModulationItems (use_modulation=False: SkipCat merges)."""
+
+    def __init__(self, in_channels: int, length: int, num_splits: int,
+                 diffusion_t: Callable = ARVDiffusion, sampler_t: Callable = ARVSampler, **kwargs):
+        super().__init__(in_channels=in_channels + 1, out_channels=in_channels,
+                         diffusion_t=diffusion_t, diffusion_length=length, diffusion_num_splits=num_splits,
+                         sampler_t=sampler_t, sampler_in_channels=in_channels, sampler_length=length,
+                         sampler_num_splits=num_splits, use_time_conditioning=False, use_modulation=False,
+                         **kwargs)
 
 
 class DiffusionUpsampler(DiffusionModel):

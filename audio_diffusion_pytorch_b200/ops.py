@@ -338,6 +338,16 @@ def inpaint_blend(x: Tensor, source: Tensor, noise: Tensor, mask_u8: Tensor, ab:
     return x
 
 
+def arv_step(chan: Tensor, v: Tensor, sig_next: Tensor) -> Tensor:
+    """In place on chan [B, C+1, T] (current | sigma_i): the ARVSampler update with per-position
+    noise levels (reference diffusion.py:231-235); channel C becomes sig_next [B, T]."""
+    B, C1, T = chan.shape
+    _launch(lambda: _lib.lib().adp_arv_step(chan.data_ptr(), v.data_ptr(), sig_next.data_ptr(), B, C1 - 1,
+                                            T, _stream()),
+            "adp_arv_step", lambda: ("arv_step", 0, 2 * _nb(chan) + _nb(v)))
+    return chan
+
+
 # ----------------------------------------------------------------------------- backward
 def pack_conv_dgrad(w: Tensor) -> Tensor:
     """Weights of the data-gradient conv: dA[t] = sum_j dOut[t + o_j] @ Wt_j with the taps

@@ -146,6 +146,8 @@ class GradSync:
         """dW_cond / db_cond averaged over ranks WITHOUT all-reducing the [47 K x 1024] matrix:
         gather the rank-B factors (dss [B, n], cond [B, 1024]) and redo the small product."""
         from . import ops
+        if plan.n_tot == 0:              # use_modulation=False: no conditioning projection
+            return
         B, Fm = plan.cond.shape
         n = plan.dss_all.shape[1]
         dss_g = torch.empty(self.world * B, n, device=plan.dss_all.device)

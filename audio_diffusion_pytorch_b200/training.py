@@ -145,13 +145,15 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         return t
 
     n_tot = P["cond_n"]
-    ss_all = _zeros((B, ops.round_up(n_tot, 8)), dev)
+    mod = net.use_modulation       # False: no ModulationItems, SkipCat merges (reference components.py:90,99)
+    ss_all = _zeros((B, max(8, ops.round_up(n_tot, 8))), dev)
     dss_all = gbuf(ss_all.shape)
     ss_stride = ss_all.shape[1]
-    cond_bias = _pad_to(P["cond_b"], ss_all.shape[1])
-    plan.fwd.append(lambda: plan.cond_bf.copy_(plan.cond.view(1, B, Fm)))
-    plan.fwd.append(lambda: ops.conv_gemm(plan.cond_bf, P["cond_w"], ss_all.view(1, B, -1), c_in=Fm,
-                                          n_valid=ss_all.shape[1], bias=cond_bias))
+    if mod:
+        cond_bias = _pad_to(P["cond_b"], ss_all.shape[1])
+        plan.fwd.append(lambda: plan.cond_bf.copy_(plan.cond.view(1, B, Fm)))
+        plan.fwd.append(lambda: ops.conv_gemm(plan.cond_bf, P["cond_w"], ss_all.view(1, B, -1), c_in=Fm,
+                                              n_valid=ss_all.shape[1], bias=cond_bias))
 
     # ---- cross-attention context: LayerNorm(embedding) once per forward (the per-item
     # norm_context affines are folded into each item's to_kv weights)
@@ -256,14 +258,18 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         bwds: List = []
         for ip, im in zip(items_p, items_m):
             r_ = im.resnet
-            ss = ss_all[:, ip["ss_off"]:]
-            dss = dss_all[:, ip["ss_off"]:]
+            ss = ss_all[:, ip["ss_off"]:] if mod else None
+            dss = dss_all[:, ip["ss_off"]:] if mod else None
             has_att, has_cross, has_inj = im.attention is not None, im.cross is not None, im.inject is not None
             h_stats = new_stats()
             y_stats = None if (has_att or has_cross or has_inj) else new_stats()
             S1, S2 = new_stats(), new_stats()
-            h, rr, y = act(B, Tl, C), act(B, Tl, C), act(B, Tl, C)
-            xn_first = act(B, Tl, C) if ((has_att or has_cross) and not has_inj) else None
+            h, rr = act(B, Tl, C), act(B, Tl, C)
+            # without a ModulationItem the ResnetItem's output is the item's output: conv2 writes
+            # it (and its GroupNorm statistics) directly
+            y = act(B, Tl, C) if mod else rr
+            rs = None if mod else y_stats
+            xn_first = act(B, Tl, C) if ((has_att or has_cross) and not has_inj and mod) else None
             dgn1 = (grad_for(r_.gn1.weight), grad_for(r_.gn1.bias))
             dgn2 = (grad_for(r_.gn2.weight), grad_for(r_.gn2.bias))
             db1, db2 = grad_for(r_.conv1.bias), grad_for(r_.conv2.bias)
@@ -276,15 +282,19 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                 db_scratch = gbuf((C,))
                 plan.fwd.append(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.narrow_conv(
                     x, h, s, ip["gn1"][0], ip["gn1"][1], ip["w1"], ip["b1"], G, stats_out=hs))
-                plan.fwd.append(lambda x=x, h=h, rr=rr, hs=h_stats, ip=ip: ops.narrow_conv(
-                    h, rr, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], ip["b2"], G, residual=x))
-                plan.fwd.append(modulation_fwd)
+                plan.fwd.append(lambda x=x, h=h, rr=rr, hs=h_stats, ip=ip, rs=rs: ops.narrow_conv(
+                    h, rr, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], ip["b2"], G, residual=x, stats_out=rs))
+                if mod:
+                    plan.fwd.append(modulation_fwd)
 
                 def bwd(dy, x=x, h=h, rr=rr, ss=ss, dss=dss, xs=x_stats, hs=h_stats, ip=ip, dr=dr,
                         dh=dh, dx=dx, dxh=dxh, S1=S1, S2=S2, dgn1=dgn1, dgn2=dgn2, dw1=dw1, dw2=dw2,
                         db1=db1, db2=db2, db_scratch=db_scratch):
-                    ops.ln_film_bwd(dy, rr, ss, ss_stride, dr, dss=dss, dss_stride=ss_stride,
-                                    eps=net.MOD_LN_EPS)
+                    if mod:
+                        ops.ln_film_bwd(dy, rr, ss, ss_stride, dr, dss=dss, dss_stride=ss_stride,
+                                        eps=net.MOD_LN_EPS)
+                    else:
+                        dr = dy
                     ops.narrow_conv_bwd(dr, h, hs, ip["gn2"][0], ip["gn2"][1], ip["w2"], dxh, dgn2[0],
                                         dgn2[1], S2, dw2, db2, G)
                     ops.gn_bwd_apply(dxh, h, hs, S2, dh, G, colsum=db1)   # fp32 sum, pre-rounding
@@ -302,9 +312,11 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                     a1, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs, groups=G))
                 plan.fwd.append(lambda a2=a2, h=h, hs=h_stats, ip=ip: ops.gn_silu(
                     h, a2, hs, ip["gn2"][0], ip["gn2"][1], G, net.GN_EPS))
-                plan.fwd.append(lambda x=x, a2=a2, rr=rr, ip=ip: ops.conv_gemm(
-                    a2, ip["w2"], rr, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
-                plan.fwd.append(modulation_fwd)
+                plan.fwd.append(lambda x=x, a2=a2, rr=rr, ip=ip, rs=rs: ops.conv_gemm(
+                    a2, ip["w2"], rr, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x,
+                    stats=rs, groups=G))
+                if mod:
+                    plan.fwd.append(modulation_fwd)
                 da = act(B, Tl, C)
                 # [tap][co][ci] accumulators of the fused 3-tap wgrad -> PyTorch [co][ci][tap]
                 gw = {"w1": grad_for(r_.conv1.weight, (3, C, C), (1, 2, 0)),
@@ -313,8 +325,12 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                 def bwd(dy, x=x, h=h, rr=rr, a1=a1, a2=a2, ss=ss, dss=dss, xs=x_stats, hs=h_stats,
                         ip=ip, dr=dr, dh=dh, dx=dx, dxh=dxh, da=da, S1=S1, S2=S2, dgn1=dgn1,
                         dgn2=dgn2, db1=db1, db2=db2, wd1=wd1, wd2=wd2, gw=gw, C=C):
-                    ops.ln_film_bwd(dy, rr, ss, ss_stride, dr, dss=dss, dss_stride=ss_stride,
-                                    colsum=db2, eps=net.MOD_LN_EPS)
+                    if mod:
+                        ops.ln_film_bwd(dy, rr, ss, ss_stride, dr, dss=dss, dss_stride=ss_stride,
+                                        colsum=db2, eps=net.MOD_LN_EPS)
+                    else:
+                        dr = dy
+                        ops.colsum(dy, db2)
                     conv3_bwd(dr, a2, gw["w2"], da, wd2, C)
                     ops.gn_silu_bwd(da, h, hs, ip["gn2"][0], ip["gn2"][1], dxh, dgn2[0], dgn2[1], S2, G)
                     ops.gn_bwd_apply(dxh, h, hs, S2, dh, G, colsum=db1)
@@ -322,8 +338,9 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
                     ops.gn_silu_bwd(da, x, xs, ip["gn1"][0], ip["gn1"][1], dxh, dgn1[0], dgn1[1], S1, G)
                     ops.gn_bwd_apply(dxh, x, xs, S1, dx, G, dres=dr)
                     return dx
-            grads[id(im.modulation.proj.weight)] = ("cond_w", ip["ss_off"], 2 * C)
-            grads[id(im.modulation.proj.bias)] = ("cond_b", ip["ss_off"], 2 * C)
+            if mod:
+                grads[id(im.modulation.proj.weight)] = ("cond_w", ip["ss_off"], 2 * C)
+                grads[id(im.modulation.proj.bias)] = ("cond_b", ip["ss_off"], 2 * C)
             chain = [bwd]
             x, x_stats = y, y_stats
             xn = xn_first
@@ -412,17 +429,48 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             x, st, inner = level(i + 1, skip, Tl)
         cur["inner_end"] = cursor[0]
         x, st, items_up_bwd = run_items(x, st, Lp["items_up"], lv.items_up, lv, Tl, li=i)
-        gate = ss_all[:, Lp["gate_off"]:]
-        dgate = dss_all[:, Lp["gate_off"]:]
-        grads[id(lv.merge.weight)] = ("cond_w", Lp["gate_off"], lv.out_ch)
-        grads[id(lv.merge.bias)] = ("cond_b", Lp["gate_off"], lv.out_ch)
-        db_up = grad_for(lv.up.bias)
+        s_cat = 2 ** -0.5
+        if mod:
+            gate = ss_all[:, Lp["gate_off"]:]
+            dgate = dss_all[:, Lp["gate_off"]:]
+            grads[id(lv.merge.weight)] = ("cond_w", Lp["gate_off"], lv.out_ch)
+            grads[id(lv.merge.bias)] = ("cond_b", Lp["gate_off"], lv.out_ch)
         x_last = x
+        if i == 0 and not mod:
+            # SkipCat at level 0 runs in the stem kernels with the 1x1 merge conv folded into both
+            # branches (B200UNet._compute_packed): they produce the gradients of the FOLDED
+            # weights, unfolded below (a few hundred numbers) into merge / up / adapter gradients
+            Co, Ci = lv.out_ch, lv.in_ch
+            gate, dgate = torch.ones(B, 8, device=dev), gbuf((B, 8))
+            dw_up, db_up = gbuf((Co, C, 3)), gbuf((Co,))
+            dwa, dba = gbuf((Co, Ci)), gbuf((Co,))
+
+            def unfold_level0():
+                wm = lv.merge.weight.detach().float()[:, :, 0]
+                wc1, wc2 = wm[:, :Co], wm[:, Co:]
+                w_up, b_up = lv.up.weight.detach().float(), lv.up.bias.detach().float()
+                grads[id(lv.up.weight)] = torch.einsum("om,ock->mck", wc2, dw_up)
+                grads[id(lv.up.bias)] = wc2.t() @ db_up
+                d_wc2 = torch.einsum("ock,mck->om", dw_up, w_up) + torch.outer(db_up, b_up)
+                if lv.adapter is not None:
+                    w_ad = lv.adapter.weight.detach().float()[:, :, 0]
+                    b_ad = lv.adapter.bias.detach().float()
+                    grads[id(lv.adapter.weight)] = s_cat * (wc1.t() @ dwa)
+                    grads[id(lv.adapter.bias)] = s_cat * (wc1.t() @ dba)
+                    d_wc1 = s_cat * (dwa @ w_ad.t() + torch.outer(dba, b_ad))
+                else:
+                    d_wc1 = s_cat * dwa
+                grads[id(lv.merge.weight)] = torch.cat([d_wc1, d_wc2], dim=1)
+                grads[id(lv.merge.bias)] = db_up.clone()
+            finals.append(unfold_level0)
+        else:
+            db_up = grad_for(lv.up.bias)
         if i == 0:
-            dw_up = grad_for(lv.up.weight)
-            dwa = (grad_for(lv.adapter.weight, (lv.out_ch, lv.in_ch, 1)).view(lv.out_ch, lv.in_ch)
-                   if lv.adapter is not None else None)
-            dba = grad_for(lv.adapter.bias) if lv.adapter is not None else None
+            if mod:
+                dw_up = grad_for(lv.up.weight)
+                dwa = (grad_for(lv.adapter.weight, (lv.out_ch, lv.in_ch, 1)).view(lv.out_ch, lv.in_ch)
+                       if lv.adapter is not None else None)
+                dba = grad_for(lv.adapter.bias) if lv.adapter is not None else None
             dh0 = act(B, Tl, C)
             plan.fwd.append(lambda: ops.stem_out(
                 x_last, plan.x, Lp["up_w"], Lp["up_b"], gate, lv.factor, append=plan.append,
@@ -502,10 +550,50 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
 
             def up_dgrad():
                 ops.conv_gemm(dys, wd_up, dx_last, c_in=Co, n_valid=C, taps=(-1, 0, 1))
-        plan.fwd.append(lambda: ops.skip_gate(y_up, x_in, gate, out, ost, G))
+        if mod:
+            plan.fwd.append(lambda: ops.skip_gate(y_up, x_in, gate, out, ost, G))
+            d_skip_of = lambda d_out: d_out      # noqa: E731  (the skip path's gradient is d_out itself)
+
+            def merge_bwd(d_out: Tensor) -> None:
+                ops.skip_gate_bwd(d_out, y_up, gate, dys, dgate)
+        else:
+            # SkipCat: out = (s Wc1) skip + Wc2 y_up + bc as two accumulating GEMMs; an 8-channel
+            # level is processed two positions per row against block-diagonal weights (K >= 16)
+            rp = max(1, 16 // Co)
+            assert T_in % rp == 0, "SkipCat merge of an 8-channel level needs an even length"
+
+            def rows(t):
+                return t.view(B, T_in // rp, rp * Co)
+            tmp, d_skip = act(B, T_in, Co), act(B, T_in, Co)
+            plan.fwd.append(lambda: ops.conv_gemm(rows(x_in), Lp["cat_w1"], rows(tmp), c_in=rp * Co,
+                                                  n_valid=rp * Co, bias=Lp["cat_b"]))
+            plan.fwd.append(lambda: ops.conv_gemm(rows(y_up), Lp["cat_w2"], rows(out), c_in=rp * Co,
+                                                  n_valid=rp * Co, residual=rows(tmp),
+                                                  stats=ost if rp == 1 else None, groups=G))
+            if rp > 1:
+                plan.fwd.append(lambda: ops.gn_stats(out, ost, G))
+            wm_ = lv.merge.weight
+            wd_c1 = packed_dgrad(lambda: ops.pack_linear(torch.block_diag(
+                *[wm_.detach().float()[:, :Co, 0].t() * s_cat] * rp).contiguous()))
+            wd_c2 = packed_dgrad(lambda: ops.pack_linear(torch.block_diag(
+                *[wm_.detach().float()[:, Co:, 0].t()] * rp).contiguous()))
+            gw_cat = grad_for(wm_, (Co, 2 * Co, 1)).view(Co, 2 * Co)
+            db_cat = grad_for(lv.merge.bias)
+            blk1, blk2 = gbuf((rp * Co, rp * Co)), gbuf((rp * Co, rp * Co))
+            d_skip_of = lambda d_out: d_skip     # noqa: E731
+
+            def merge_bwd(d_out: Tensor) -> None:
+                ops.colsum(d_out, db_cat)
+                ops.wgrad(rows(d_out), rows(x_in), blk1, n=rp * Co, k=rp * Co)
+                ops.wgrad(rows(d_out), rows(y_up), blk2, n=rp * Co, k=rp * Co)
+                # the diagonal blocks of the paired-position products sum to the 1x1 conv's gradient
+                gw_cat[:, :Co].copy_(blk1.view(rp, Co, rp, Co).diagonal(dim1=0, dim2=2).sum(-1) * s_cat)
+                gw_cat[:, Co:].copy_(blk2.view(rp, Co, rp, Co).diagonal(dim1=0, dim2=2).sum(-1))
+                ops.conv_gemm(rows(d_out), wd_c2, rows(dys), c_in=rp * Co, n_valid=rp * Co)
+                ops.conv_gemm(rows(d_out), wd_c1, rows(d_skip), c_in=rp * Co, n_valid=rp * Co)
 
         def backward_level(d_out: Tensor) -> Tensor:
-            ops.skip_gate_bwd(d_out, y_up, gate, dys, dgate)
+            merge_bwd(d_out)
             ops.colsum(dys, db_up)
             up_wgrad()
             up_dgrad()
@@ -523,7 +611,7 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
             plan.mark((cur["entry"], cur["down_end"] if inner is not None else cur["exit"]))
             # gradient w.r.t. the level input = dgrad(down conv) + the skip path (d_out)
             ops.conv_gemm(d, wd_down, d_xin.view(B, Tl, kdim), c_in=C, n_valid=kdim,
-                          residual=d_out.view(B, Tl, kdim))
+                          residual=d_skip_of(d_out).view(B, Tl, kdim))
             return d_xin
 
         cur["exit"] = cursor[0]
@@ -550,8 +638,9 @@ def build_train_plan(net: B200UNet, B: int, T: int, M: int, mode: str, want_dxin
         if den is not None:      # d embedding = LayerNorm backward of the summed context gradients
             ops.ln_film_bwd(den, plan.embedding, None, 0, plan.demb, eps=net.ATT_LN_EPS)
         plan.dcond.zero_()
-        ops.cond_bwd(dss_all, plan.cond_bf.view(B, Fm).float(), P["cond_w"], plan.dw_all,
-                     plan.dbias_all, plan.dcond, n_tot)
+        if mod:
+            ops.cond_bwd(dss_all, plan.cond_bf.view(B, Fm).float(), P["cond_w"], plan.dw_all,
+                         plan.dbias_all, plan.dcond, n_tot)
     plan.backward_program = backward_program
     plan.P, plan.n_dss = P, dss_all.numel()
     return plan
@@ -788,6 +877,9 @@ def _time_cond(net: B200UNet, sigmas: Optional[Tensor], features: Optional[Tenso
         f = F.gelu(t.mlp(F.gelu(t.mlp(F.gelu(emb)))))
         if features is not None:
             f = f + features
+    elif not net.use_modulation:         # no ModulationItems: nothing consumes the features
+        ref = next(net.parameters())
+        return torch.zeros(1, net.features, device=ref.device)
     else:
         assert features is not None, "use_time_conditioning=False needs features="
         f = features

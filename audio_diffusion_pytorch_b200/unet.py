@@ -71,10 +71,10 @@ class ItemParams(nn.Module):
 
     def __init__(self, channels: int, groups: int, features: int, att: bool, cross: bool,
                  head_features: Optional[int], heads: Optional[int],
-                 embedding_features: Optional[int], context: int = 0):
+                 embedding_features: Optional[int], context: int = 0, modulation: bool = True):
         super().__init__()
         self.resnet = ResnetParams(channels, groups)
-        self.modulation = ModulationParams(channels, features)
+        self.modulation = ModulationParams(channels, features) if modulation else None
         # a_unet InjectChannelsItem: Conv1d(C + ctx -> C, k=1) over cat([x, channels[depth]]), + x
         self.inject = nn.Conv1d(channels + context, channels, 1) if context > 0 else None
         self.attention = AttentionParams(channels, head_features, heads) if att else None
@@ -94,7 +94,10 @@ class LevelParams(nn.Module):
         self.inner = inner
         self.items_up = nn.ModuleList([ItemParams(ch, **item_kw) for _ in range(n_items)])
         self.up = nn.Conv1d(ch, out_ch, 3, padding=1)
-        self.merge = nn.Linear(item_kw["features"], out_ch)
+        # a_unet SkipModulate (MergeModulate: Linear(features -> out)) or, with use_modulation=False,
+        # SkipCat (MergeCat: Conv1d(2*out -> out, k=1) over cat([skip * 2^-0.5, y]))
+        self.merge = (nn.Linear(item_kw["features"], out_ch) if item_kw.get("modulation", True)
+                      else nn.Conv1d(2 * out_ch, out_ch, 1))
         self.in_ch, self.out_ch, self.ch, self.factor = in_ch, out_ch, ch, factor
 
 
@@ -187,8 +190,6 @@ class B200UNet(nn.Module):
             raise NotImplementedError(
                 "use_text_conditioning builds a T5 encoder (a_unet TextConditioningPlugin); pass "
                 "precomputed `embedding=` with use_text_conditioning=False (SURVEY.md 3.4)")
-        if not use_modulation:
-            raise NotImplementedError("use_modulation=False (SkipCat) is outside the B200 hot path")
         for c, ctx in zip(channels, context_channels):
             assert ctx == 0 or c >= 16, "InjectChannelsItem is built for levels with >= 16 channels"
         if any(attentions) or any(cross_attentions):
@@ -208,6 +209,7 @@ class B200UNet(nn.Module):
         self.heads, self.head_features = attention_heads, attention_features
         self.embedding_features = embedding_features
         self.use_time_conditioning, self.use_embedding_cfg = use_time_conditioning, use_embedding_cfg
+        self.use_modulation = use_modulation
         for c in self.channels:
             assert c % resnet_groups == 0 and c % 8 == 0, "channels must be multiples of 8 and groups"
         assert self.out_channels <= 4 and self.in_channels <= 8, "stem kernels: in<=8, out<=4 channels"
@@ -226,7 +228,8 @@ class B200UNet(nn.Module):
                                groups=resnet_groups, features=modulation_features,
                                att=bool(attentions[i]), cross=bool(cross_attentions[i]),
                                head_features=attention_features, heads=attention_heads,
-                               embedding_features=embedding_features, context=context_channels[i])
+                               embedding_features=embedding_features, context=context_channels[i],
+                               modulation=use_modulation)
 
         self.net = build(0)
         self._plans: Dict[Tuple, _Plan] = {}
@@ -385,8 +388,9 @@ class B200UNet(nn.Module):
             r = it.resnet
             d: Dict = {"gn1": (f32(r.gn1.weight), f32(r.gn1.bias)),
                        "gn2": (f32(r.gn2.weight), f32(r.gn2.bias)),
-                       "b1": f32(r.conv1.bias), "b2": f32(r.conv2.bias),
-                       "ss_off": add_cond(it.modulation.proj)}
+                       "b1": f32(r.conv1.bias), "b2": f32(r.conv2.bias)}
+            if it.modulation is not None:
+                d["ss_off"] = add_cond(it.modulation.proj)
             if narrow:
                 d["w1"], d["w2"] = f32(r.conv1.weight), f32(r.conv2.weight)
             else:
@@ -423,14 +427,43 @@ class B200UNet(nn.Module):
                              if lvl.factor > 1 else ops.pack_conv(lvl.up.weight.detach()))
             L["items_down"] = [pack_item(it, narrow) for it in lvl.items_down]
             L["items_up"] = [pack_item(it, narrow) for it in lvl.items_up]
-            L["gate_off"] = add_cond(lvl.merge)
+            if self.use_modulation:
+                L["gate_off"] = add_cond(lvl.merge)
+            else:
+                # SkipCat: out = Wc1 (skip * s) + Wc2 y + bc,  W = [Wc1 | Wc2]
+                s_ = 2 ** -0.5
+                wm = lvl.merge.weight.detach().float()[:, :, 0]
+                co = wm.shape[0]
+                wc1, wc2, bc = wm[:, :co] * s_, wm[:, co:], lvl.merge.bias.detach().float()
+                if i > 0:
+                    # the tensor-core GEMM needs K >= 16: an 8-channel level output is viewed as
+                    # [B, T/2, 16] (two positions per row) against block-diagonal weights
+                    rr = max(1, 16 // co)
+                    L["cat_w1"] = ops.pack_linear(torch.block_diag(*[wc1] * rr))
+                    L["cat_w2"] = ops.pack_linear(torch.block_diag(*[wc2] * rr))
+                    L["cat_b"] = bc.repeat(rr).contiguous()
+                else:
+                    # level 0 runs in the stem kernel (skip adapter + upsample conv + merge): fold the
+                    # 1x1 merge conv into both branches.  v = (Wc1 W_ad) x + Wc1 b_ad + conv'(h) + b',
+                    # conv' = Wc2 o W_up, b' = Wc2 b_up + bc; the kernel's gate is 1.
+                    w_up = lvl.up.weight.detach().float()
+                    L["up_w"] = torch.einsum("om,mck->ock", wc2, w_up).contiguous()
+                    L["up_b"] = (wc2 @ lvl.up.bias.detach().float() + bc).contiguous()
+                    if lvl.adapter is not None:
+                        L["adapt_w"] = (wc1 @ lvl.adapter.weight.detach().float()[:, :, 0]).contiguous()
+                        L["adapt_b"] = (wc1 @ lvl.adapter.bias.detach().float()).contiguous()
+                    else:
+                        L["adapt_w"], L["adapt_b"] = wc1.contiguous(), torch.zeros_like(bc)
             P["levels"].append(L)
         n_tot = off
-        w_all = torch.cat(cond_w, 0)
-        n_pad = ops.round_up(n_tot, 256)
-        w_pad = torch.zeros(n_pad, w_all.shape[1], dtype=torch.bfloat16, device=w_all.device)
-        w_pad[:n_tot] = w_all.to(torch.bfloat16)
-        P["cond_w"], P["cond_b"], P["cond_n"] = w_pad.contiguous(), torch.cat(cond_b).contiguous(), n_tot
+        if cond_w:
+            w_all = torch.cat(cond_w, 0)
+            n_pad = ops.round_up(n_tot, 256)
+            w_pad = torch.zeros(n_pad, w_all.shape[1], dtype=torch.bfloat16, device=w_all.device)
+            w_pad[:n_tot] = w_all.to(torch.bfloat16)
+            P["cond_w"], P["cond_b"], P["cond_n"] = w_pad.contiguous(), torch.cat(cond_b).contiguous(), n_tot
+        else:          # use_modulation=False: no conditioning linears at all
+            P["cond_w"], P["cond_b"], P["cond_n"] = None, None, 0
         if self.time is not None:
             t = self.time
             kdim = t.to_out.weight.shape[1]
@@ -483,6 +516,12 @@ class B200UNet(nn.Module):
         R = sigmas.shape[0]
         key = ("cond", R)
         self.packed()
+        if not self.use_modulation:       # nothing to evaluate: a dummy table keeps the step selector uniform
+            plan = self._plans.get(key)
+            if plan is None:
+                plan = self._plans[key] = _Plan()
+                plan.ss_all = torch.zeros(R, 8, device=sigmas.device)
+            return plan.ss_all
         plan = self._plans.get(key)
         if plan is None:
             ops.device_check()
@@ -554,13 +593,17 @@ class B200UNet(nn.Module):
         # The sampler knows every sigma_i up front and evaluates this ONCE for all steps
         # (_cond_table): its plan only receives the step's rows of the table.
         if mode == "sample":
-            ss_all = torch.zeros(Bh, ops.round_up(P["cond_n"], 8), device=dev)
+            ss_all = torch.zeros(Bh, max(8, ops.round_up(P["cond_n"], 8)), device=dev)
             plan.ss_all = ss_all
             plan.use_features_in = False
             plan.add(lambda: ops.step_select(plan.step, plan.ctrl, plan.ab_table, plan.ab, ss_all))
-        else:
+        elif self.use_modulation:
             ss_all = self._add_conditioning(plan, P, Bh)
+        else:
+            ss_all = torch.zeros(Bh, 8, device=dev)
+            plan.use_features_in = False
         ss_stride = ss_all.shape[1]
+        mod = self.use_modulation
 
         # ---- one item chain
         def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], lv: LevelParams, Tl: int,
@@ -571,7 +614,7 @@ class B200UNet(nn.Module):
             # instead of gn_silu -> conv_gemm (-> ln_film)
             thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 4 == 0)
             for idx, ip in enumerate(items_p):
-                ss = ss_all[:, ip["ss_off"]:]
+                ss = ss_all[:, ip["ss_off"]:] if mod else None
                 has_att, has_cross, has_inj = "att" in ip, "cross" in ip, "inj" in ip
                 item_last = idx == len(items_p) - 1
                 want_stats = (not item_last) or last_needs_stats
@@ -593,15 +636,18 @@ class B200UNet(nn.Module):
                 else:
                     h = pool.get(Bh, Tl, C)
                     r = pool.get(Bh, Tl, C)
-                    y = pool.get(Bh, Tl, C)
+                    y = pool.get(Bh, Tl, C) if mod else None
+                    # use_modulation=False: the ResnetItem's output IS the item's output, so its
+                    # GroupNorm statistics come out of conv2's epilogue
+                    rs = None if mod else mod_stats
                     if self.fuse_groupnorm:
                         # ConvBlock = ONE kernel: GroupNorm+SiLU applied to the smem A tile
                         plan.add(lambda x=x, h=h, s=x_stats, hs=h_stats, ip=ip: ops.conv_gemm(
                             x, ip["w1"], h, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b1"], stats=hs,
                             groups=G, gn=(s, ip["gn1"][0], ip["gn1"][1], G, self.GN_EPS)))
-                        plan.add(lambda x=x, h=h, r=r, hs=h_stats, ip=ip: ops.conv_gemm(
+                        plan.add(lambda x=x, h=h, r=r, hs=h_stats, ip=ip, rs=rs: ops.conv_gemm(
                             h, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x,
-                            gn=(hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS)))
+                            stats=rs, groups=G, gn=(hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS)))
                     else:
                         a = pool.get(Bh, Tl, C)
                         plan.add(lambda x=x, a=a, s=x_stats, ip=ip: ops.gn_silu(
@@ -611,15 +657,19 @@ class B200UNet(nn.Module):
                             groups=G))
                         plan.add(lambda a=a, h=h, hs=h_stats, ip=ip: ops.gn_silu(
                             h, a, hs, ip["gn2"][0], ip["gn2"][1], G, self.GN_EPS))
-                        plan.add(lambda x=x, a=a, r=r, ip=ip: ops.conv_gemm(
-                            a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x))
+                        plan.add(lambda x=x, a=a, r=r, ip=ip, rs=rs: ops.conv_gemm(
+                            a, ip["w2"], r, c_in=C, n_valid=C, taps=(-1, 0, 1), bias=ip["b2"], residual=x,
+                            stats=rs, groups=G))
                         pool.put(a)
-                    xn_first = pool.get(Bh, Tl, C) if ((has_att or has_cross) and not has_inj) else None
-                    # Modulation and the following attention pre-norm in ONE pass over the rows
-                    plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats, xn=xn_first: ops.ln_film(
-                        r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS, y2=xn, eps2=self.ATT_LN_EPS))
+                    xn_first = pool.get(Bh, Tl, C) if ((has_att or has_cross) and not has_inj and mod) else None
+                    if mod:
+                        # Modulation and the following attention pre-norm in ONE pass over the rows
+                        plan.add(lambda r=r, y=y, ss=ss, ms=mod_stats, xn=xn_first: ops.ln_film(
+                            r, y, ss, ss_stride, ms, G, self.MOD_LN_EPS, y2=xn, eps2=self.ATT_LN_EPS))
+                        pool.put(r)
+                    else:
+                        y = r
                     pool.put(h)
-                    pool.put(r)
                 # the item's input is dead now (a level's skip is the chain's *output*)
                 pool.put(x)
                 x, x_stats = y, mod_stats
@@ -709,14 +759,41 @@ class B200UNet(nn.Module):
                 x, st = run_level(i + 1, skip, Tl)
                 pool.put(skip)
             x, st = run_items(x, st, Lp["items_up"], lv, Tl, last_needs_stats=False, li=i)
-            gate = ss_all[:, Lp["gate_off"]:]
+            gate = ss_all[:, Lp["gate_off"]:] if mod else None
             if i == 0:
                 plan.h0 = x
-                plan.gate0 = gate
+                plan.gate0 = gate if mod else torch.ones(Bh, 8, device=dev)
                 plan.level0 = (lv, Lp)
                 return x, None
             out = pool.get(Bh, T_in, lv.out_ch)
             ost = new_stats()
+            if not mod:
+                # SkipCat: y = upsample conv (+ bias); tmp = Wc1 (skip * s) + bc; out = Wc2 y + tmp
+                Co = lv.out_ch
+                rr = max(1, 16 // Co)
+                assert T_in % rr == 0, "SkipCat merge of an 8-channel level needs an even length"
+                y_up, tmp = pool.get(Bh, T_in, Co), pool.get(Bh, T_in, Co)
+
+                def rows(t, rr=rr, Co=Co):
+                    return t.view(Bh, T_in // rr, rr * Co)
+                if lv.factor > 1:
+                    plan.add(lambda x=x, y_up=y_up: ops.conv_gemm(
+                        x, Lp["up_w"], y_up.view(Bh, Tl, lv.factor * lv.out_ch), c_in=C, n_valid=lv.out_ch,
+                        up_factor=lv.factor, bias=Lp["up_b"]))
+                else:
+                    plan.add(lambda x=x, y_up=y_up: ops.conv_gemm(
+                        x, Lp["up_w"], y_up, c_in=C, n_valid=lv.out_ch, taps=(-1, 0, 1), bias=Lp["up_b"]))
+                plan.add(lambda tmp=tmp: ops.conv_gemm(rows(x_in), Lp["cat_w1"], rows(tmp), c_in=rr * Co,
+                                                      n_valid=rr * Co, bias=Lp["cat_b"]))
+                plan.add(lambda y_up=y_up, tmp=tmp, out=out, ost=ost: ops.conv_gemm(
+                    rows(y_up), Lp["cat_w2"], rows(out), c_in=rr * Co, n_valid=rr * Co, residual=rows(tmp),
+                    stats=ost if rr == 1 else None, groups=G))
+                if rr > 1:           # the epilogue's group mapping does not see the paired layout
+                    plan.add(lambda out=out, ost=ost: ops.gn_stats(out, ost, G))
+                pool.put(y_up)
+                pool.put(tmp)
+                pool.put(x)
+                return out, ost
             if lv.factor > 1:
                 plan.add(lambda x=x, out=out, ost=ost: ops.conv_gemm(
                     x, Lp["up_w"], out.view(Bh, Tl, lv.factor * lv.out_ch), c_in=C, n_valid=lv.out_ch,
@@ -858,7 +935,7 @@ class B200UNet(nn.Module):
             if cfg:
                 plan.sigma[B:].copy_(time.reshape(-1))
             plan.use_features_in = exists(features)
-        else:
+        elif self.use_modulation:
             assert exists(features), "use_time_conditioning=False needs features="
         if exists(features):
             plan.features_in[:B].copy_(features)
@@ -1009,6 +1086,39 @@ def _inpaint_loop(self, x_noisy: Tensor, source: Tensor, mask: Tensor, sigmas: T
 
 
 B200UNet.inpaint_loop = torch.no_grad()(_inpaint_loop)
+
+
+def _arv_loop(self, current: Tensor, sigmas: Tensor, progress=None, **kwargs) -> Tensor:
+    """ARVSampler.sample_loop (reference diffusion.py:223-238): the net input is cat([current,
+    sigma_i]) with a noise level PER POSITION (sigmas [N+1, B, 1, T]) and no time conditioning.
+    The plan's input buffer holds that concatenation for the whole loop: one graph launch (the
+    net) + one adp_arv_step (the update, which also writes sigma_{i+1} into the last channel)."""
+    assert current.is_cuda, "the B200 path runs on a CUDA device only (no CPU fallback)"
+    self._check_untracked_updates()
+    embedding = kwargs.get("embedding")
+    scale = kwargs.get("embedding_scale", 1.0)
+    B, C, T = current.shape
+    assert C + 1 == self.x_channels and sigmas.shape[1:] == (B, 1, T)
+    plan_x = torch.cat([current.float(), sigmas[0].float()], dim=1)
+    _, _, Bh, M = self._shape_key(plan_x, embedding, scale)
+    plan = self._plan(B, T, Bh, M, "v", (float(scale) if Bh != B else None, exists(kwargs.get("features"))))
+    self._stage_inputs(plan, plan_x, None, kwargs.get("features"), embedding, scale,
+                       kwargs.get("embedding_mask_proba", 0.0), kwargs.get("append_channels"),
+                       kwargs.get("channels"))
+    sig = sigmas.float().reshape(sigmas.shape[0], B, T).contiguous()
+    it = iter(progress) if progress is not None else None
+    for i in range(sigmas.shape[0] - 1):
+        if it is not None:
+            next(it)
+        self._execute(plan)
+        ops.arv_step(plan.x, plan.v, sig[i + 1])
+    if it is not None:
+        for _ in it:
+            pass
+    return plan.x[:, :C].clone().to(current.dtype)
+
+
+B200UNet.arv_loop = torch.no_grad()(_arv_loop)
 
 
 def _copy_tree(dst, src) -> None:

@@ -237,6 +237,13 @@ int adp_step_advance(int32_t* step, adp_stream_t stream);
 int adp_inpaint_blend(float* x, const float* source, const float* noise, const uint8_t* mask,
                       const float* ab, int64_t n, adp_stream_t stream);
 
+/* ARVSampler step (reference diffusion.py:231-235), per-position noise levels.  chan fp32
+ * [B, C+1, T] = the net input (channels 0..C-1 = current, channel C = sigma_i); v fp32 [B, C, T]
+ * = the net output; sig_next fp32 [B, T] = sigma_{i+1}.  In place: current <- alpha_{i+1} x_pred +
+ * beta_{i+1} noise_pred (alpha = cos(sigma pi/2), beta = sin(sigma pi/2)), channel C <- sig_next. */
+int adp_arv_step(float* chan, const float* v, const float* sig_next, int B, int C, int T,
+                 adp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Backward (training) entry points: VDiffusion loss.backward() through UNetV0
  * (reference diffusion.py:82-95 + autograd over the a_unet blocks).  Data gradients are

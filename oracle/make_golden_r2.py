@@ -173,12 +173,56 @@ def case_tiny_autoencoder():
                         param_fingerprint=fingerprint(m_port))
 
 
+def case_tiny_autoregressive():
+    """DiffusionAR (models.py:227-250): use_modulation=False net (SkipCat merges, no time
+    conditioning) + ARVDiffusion loss / gradients + ARVSampler (start window + 2 ladder shifts)."""
+    cfg = dict(TINY, in_channels=2, length=4096, num_splits=4)
+    torch.manual_seed(0)
+    m_ref = ref.DiffusionAR(net_t=ref.UNetV0, **cfg)
+    torch.manual_seed(0)
+    m_port = port.DiffusionARPort(**cfg)
+    same(torch.cat([p.flatten() for p in m_ref.parameters()]),
+         torch.cat([p.flatten() for p in m_port.parameters()]), "same-seed construction")
+    g = torch.Generator().manual_seed(25)
+    audio = torch.randn(2, 2, 4096, generator=g)
+    chan = torch.cat([audio, torch.rand(2, 1, 4096, generator=g)], dim=1)
+    with torch.no_grad():
+        v_ref = m_ref.net(chan)
+        same(m_port.net(chan), v_ref, "net forward (use_modulation=False)")
+    torch.manual_seed(7)
+    l_ref = m_ref(audio)
+    l_ref.backward()
+    torch.manual_seed(7)
+    l_port = m_port(audio)
+    l_port.backward()
+    same(l_port.detach(), l_ref.detach(), "ARVDiffusion loss")
+    for (n, p), q in zip(m_ref.named_parameters(), m_port.parameters()):
+        assert torch.equal(p.grad, q.grad), n
+    print("  port == reference (bit-exact): every parameter gradient")
+    torch.manual_seed(9)
+    s_ref = m_ref.sample(num_items=2, num_chunks=6, num_steps=4)
+    torch.manual_seed(9)
+    s_port = m_port.sample(num_items=2, num_chunks=6, num_steps=4)
+    same(s_port, s_ref, "ARVSampler 6 chunks (4 start + 2 shifts), 4 steps")
+    lad_ref = m_ref.sampler.get_sigmas_ladder(num_items=2, num_steps_per_split=3)
+    same(m_port.sampler.sigmas_ladder(2, 3), lad_ref, "sigma ladder")
+    names = dict(m_ref.net.named_parameters())
+    grads = {k.replace(".", "_"): v.grad.numpy() for k, v in names.items()}
+    np.savez_compressed(os.path.join(OUT, "tiny_autoregressive.npz"), input_seed=25, loss_seed=7,
+                        sample_seed=9, v=v_ref.numpy(), loss=l_ref.detach().numpy(), sample=s_ref.numpy(),
+                        ladder3=lad_ref[:, 0, 0].numpy(), param_fingerprint=fingerprint(m_port),
+                        grad_names=np.array(list(names.keys())),
+                        grad_norms=np.array([float(v.grad.norm()) for v in names.values()]),
+                        **{"grad_" + k: v for k, v in grads.items()
+                           if any(t in k for t in ("skip_merge", "skip_adapter", "block_0", "block_6"))})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     only = sys.argv[1:]
-    for case in (case_tiny_50_steps, case_tiny_inpaint, case_tiny_autoencoder, case_cfg3_readme_scale,
-                 case_readme_full_size):
+    for case in (case_tiny_50_steps, case_tiny_inpaint, case_tiny_autoencoder, case_tiny_autoregressive,
+                 case_cfg3_readme_scale, case_readme_full_size):
         if only and case.__name__ not in only:
             continue
         print(case.__name__)

@@ -222,18 +222,101 @@ class VInpainterPort(nn.Module):
         return x_noisy
 
 
+class ARVDiffusionPort(nn.Module):
+    """diffusion.py:98-130 (ARVDiffusion): one sigma per split, carried as an extra input channel.
+    RNG order: rand((B,1,num_splits)) then randn_like(x)."""
+
+    def __init__(self, net: nn.Module, length: int, num_splits: int, loss_fn=F.mse_loss):
+        super().__init__()
+        assert length % num_splits == 0, "length must be divisible by num_splits"       # :101
+        self.net, self.length, self.num_splits, self.loss_fn = net, length, num_splits, loss_fn
+        self.split_length = length // num_splits
+
+    def forward(self, x: Tensor, **kwargs) -> Tensor:
+        b, _, t = x.shape
+        assert t == self.length, "input length must match length"                       # :116
+        sigmas = torch.rand((b, 1, self.num_splits), device=x.device, dtype=x.dtype)    # :118
+        sigmas = sigmas.repeat_interleave(self.split_length, dim=2)                     # :119
+        noise = torch.randn_like(x)                                                     # :121
+        alphas, betas = half_circle(sigmas)                                             # :123
+        x_noisy = alphas * x + betas * noise                                            # :124
+        v_target = alphas * noise - betas * x                                           # :125
+        v_pred = self.net(torch.cat([x_noisy, sigmas], dim=1), **kwargs)                # :127-129
+        return self.loss_fn(v_pred, v_target)                                           # :130
+
+
+class ARVSamplerPort(nn.Module):
+    """diffusion.py:193-298 (ARVSampler)."""
+
+    def __init__(self, net: nn.Module, in_channels: int, length: int, num_splits: int):
+        super().__init__()
+        assert length % num_splits == 0, "length must be divisible by num_splits"       # :196
+        self.net, self.in_channels, self.length, self.num_splits = net, in_channels, length, num_splits
+        self.split_length = length // num_splits
+
+    @property
+    def device(self):
+        return next(self.net.parameters()).device
+
+    def sigmas_ladder(self, num_items: int, num_steps_per_split: int) -> Tensor:       # :213-221
+        b, n_half, l, k = num_items, self.num_splits // 2, self.split_length, num_steps_per_split
+        line = torch.linspace(1, 0, k * n_half, device=self.device)                     # :216
+        out = torch.zeros(k + 1, b, 1, n_half * l, device=self.device)                  # (+ index k, :219)
+        for step in range(k):                 # "(n i) -> i b 1 (n l)" then flip of the last axis (:217-218)
+            for split in range(n_half):
+                hi = n_half * l - split * l
+                out[step, :, :, hi - l:hi] = line[split * k + step]
+        out[-1, :, :, l:] = out[0, :, :, :-l]                                           # :220
+        return torch.cat([torch.zeros_like(out), out], dim=-1)                          # :221
+
+    def sample_loop(self, current: Tensor, sigmas: Tensor, **kwargs) -> Tensor:         # :223-238
+        alphas, betas = half_circle(sigmas)
+        for i in range(sigmas.shape[0] - 1):
+            v = self.net(torch.cat([current, sigmas[i]], dim=1), **kwargs)              # :231-232
+            x_pred = alphas[i] * current - betas[i] * v                                 # :233
+            n_pred = betas[i] * current + alphas[i] * v                                 # :234
+            current = alphas[i + 1] * x_pred + betas[i + 1] * n_pred                    # :235
+        return current
+
+    def sample_start(self, num_items: int, num_steps: int, **kwargs) -> Tensor:         # :240-247
+        b, c, t = num_items, self.in_channels, self.length
+        sigmas = torch.linspace(1, 0, num_steps + 1, device=self.device)
+        sigmas = sigmas.view(-1, 1, 1, 1).expand(-1, b, 1, t)
+        noise = torch.randn((b, c, t), device=self.device) * sigmas[0]
+        return self.sample_loop(current=noise, sigmas=sigmas, **kwargs)
+
+    @torch.no_grad()
+    def forward(self, num_items: int, num_chunks: int, num_steps: int, start=None,
+                show_progress: bool = False, **kwargs) -> Tensor:                       # :250-298
+        n = self.num_splits
+        assert num_chunks >= n, f"required at least {n} chunks"
+        start = self.sample_start(num_items=num_items, num_steps=num_steps, **kwargs)
+        if num_chunks == n:
+            return start
+        assert num_steps >= n, "num_steps must be greater than num_splits"
+        sigmas = self.sigmas_ladder(num_items, num_steps // n)
+        alphas, betas = half_circle(sigmas)
+        start_noise = alphas[0] * start + betas[0] * torch.randn_like(start)            # :278
+        chunks = list(start_noise.chunk(chunks=n, dim=-1))
+        for _ in range(num_chunks):                                                     # :282
+            updated = self.sample_loop(current=torch.cat(chunks[-n:], dim=-1), sigmas=sigmas, **kwargs)
+            chunks[-n:] = list(updated.chunk(chunks=n, dim=-1))
+            chunks += [torch.randn((num_items, self.in_channels, self.split_length), device=self.device)]
+        return torch.cat(chunks[:num_chunks], dim=-1)                                   # :298
+
+
 # ---------------------------------------------------------------------------- models.py
 class DiffusionModelPort(nn.Module):
     """models.py:22-45 (DiffusionModel): one net shared by diffusion and sampler."""
 
     def __init__(self, net_t: Callable = build_unet_v0, loss_fn=F.mse_loss, dim: int = 1,
-                 **kwargs):
+                 diffusion_t: Callable = VDiffusionPort, sampler_t: Callable = VSamplerPort, **kwargs):
         super().__init__()
         diffusion_kw, kwargs = split_prefixed("diffusion_", kwargs)                   # :33
         sampler_kw, kwargs = split_prefixed("sampler_", kwargs)                       # :34
         self.net = net_t(dim=dim, **kwargs)                                           # :36
-        self.diffusion = VDiffusionPort(net=self.net, loss_fn=loss_fn, **diffusion_kw)
-        self.sampler = VSamplerPort(net=self.net, **sampler_kw)
+        self.diffusion = diffusion_t(net=self.net, loss_fn=loss_fn, **diffusion_kw)
+        self.sampler = sampler_t(net=self.net, **sampler_kw)
 
     def forward(self, *args, **kwargs) -> Tensor:
         return self.diffusion(*args, **kwargs)
@@ -275,6 +358,19 @@ class DiffusionAEPort(DiffusionModelPort):
         channels = [None] * self.inject_depth + [latent]
         out = super().sample(noise, channels=channels, **kwargs)
         return self.adapter.decode(out) if self.adapter is not None else out
+
+
+class DiffusionARPort(DiffusionModelPort):
+    """models.py:227-250 (DiffusionAR): net input = waveform + sigma channel, no time
+    conditioning, no modulation (SkipCat merges)."""
+
+    def __init__(self, in_channels: int, length: int, num_splits: int, **kwargs):
+        super().__init__(in_channels=in_channels + 1, out_channels=in_channels,
+                         diffusion_t=ARVDiffusionPort, diffusion_length=length,
+                         diffusion_num_splits=num_splits, sampler_t=ARVSamplerPort,
+                         sampler_in_channels=in_channels, sampler_length=length,
+                         sampler_num_splits=num_splits, use_time_conditioning=False,
+                         use_modulation=False, **kwargs)
 
 
 class ToyEncoder(nn.Module):

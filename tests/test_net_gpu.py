@@ -336,3 +336,38 @@ def test_autoencoder_decode_vs_golden(adp, oracle_port, golden_dir):
     print(f"DiffusionAE decode (3 steps, latent injected at depth 2): rel-L2 {e:.3e}")
     assert e <= 5e-3
     assert model.decode(latent, num_steps=2).shape == (2, 2, 4096)      # closest_power_2(256 * 16)
+
+
+TINY_AR = dict(TINY, in_channels=2, length=4096, num_splits=4)
+
+
+def test_autoregressive_net_and_sampler_vs_golden(adp, oracle_port, golden_dir, monkeypatch):
+    """DiffusionAR (reference models.py:227-250): the use_modulation=False net (SkipCat merges,
+    sigma as an input channel) and ARVSampler (reference diffusion.py:193-298: start window +
+    2 ladder shifts, 4 steps) against the unmodified reference.  torch.randn / randn_like are fed
+    the reference run's CPU draws."""
+    g = load(golden_dir, "tiny_autoregressive.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionARPort(**TINY_AR)
+    np.testing.assert_allclose(fingerprint(ref), g["param_fingerprint"], rtol=1e-9)
+    model = adp.DiffusionAR(net_t=adp.UNetV0, **TINY_AR).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    audio = torch.randn(2, 2, 4096, generator=gen)
+    chan = torch.cat([audio, torch.rand(2, 1, 4096, generator=gen)], dim=1)
+    for _ in range(3):                       # eager, capture, replay
+        v = model.net(chan.to(DEV))
+    e = rel_l2(v, torch.from_numpy(g["v"]))
+    print(f"use_modulation=False net forward: rel-L2 {e:.3e}")
+    assert e <= 5e-3
+    # draws of the reference run, in order: randn(start window), randn_like(start), one randn per shift
+    torch.manual_seed(int(g["sample_seed"]))
+    draws = iter([torch.randn(2, 2, 4096), torch.randn(2, 2, 4096)] + [torch.randn(2, 2, 1024) for _ in range(6)])
+    monkeypatch.setattr(torch, "randn", lambda *a, **kw: next(draws).to(kw.get("device", "cpu")))
+    monkeypatch.setattr(torch, "randn_like", lambda t_, **kw: next(draws).to(t_))
+    out = model.sample(num_items=2, num_chunks=6, num_steps=4)
+    monkeypatch.undo()
+    assert out.shape == (2, 2, 6144)
+    e = rel_l2(out, torch.from_numpy(g["sample"]))
+    print(f"ARVSampler 6 chunks x 4 steps: rel-L2 {e:.3e}")
+    assert e <= 1e-2

@@ -189,3 +189,44 @@ def test_oracle_autoencoder(oracle_port, golden_dir):
     latent = m.encoder(audio).detach()
     out = m.decode(latent, num_steps=3, generator=torch.Generator().manual_seed(int(g["decode_seed"])))
     assert rel_l2(out, t(g["decode3"])) <= 10 * RTOL
+
+
+TINY_AR = dict(TINY, in_channels=2, length=4096, num_splits=4)
+
+
+def test_oracle_autoregressive(oracle_port, golden_dir):
+    """tiny_autoregressive.npz: DiffusionAR = use_modulation=False net (SkipCat merges) with
+    ARVDiffusion loss / gradients and the ARVSampler ladder (start window + 2 shifts)."""
+    g = load(golden_dir, "tiny_autoregressive.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionARPort(**TINY_AR)
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    audio = torch.randn(2, 2, 4096, generator=gen)
+    chan = torch.cat([audio, torch.rand(2, 1, 4096, generator=gen)], dim=1)
+    with torch.no_grad():
+        assert rel_l2(m.net(chan), t(g["v"])) <= RTOL
+    torch.manual_seed(int(g["loss_seed"]))
+    loss = m(audio)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    norms = np.array([float(p.grad.norm()) for p in m.net.parameters()])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-7)
+    assert rel_l2(list(m.net.parameters())[-2].grad, t(g["grad_net_skip_merge_blocks_0_weight"])) <= 10 * RTOL
+    torch.manual_seed(int(g["sample_seed"]))
+    out = m.sample(num_items=2, num_chunks=6, num_steps=4)
+    assert out.shape == (2, 2, 6 * 1024)
+    assert rel_l2(out, t(g["sample"])) <= 10 * RTOL
+    assert torch.equal(m.sampler.sigmas_ladder(2, 3)[:, 0, 0], t(g["ladder3"]))
+
+
+def test_package_sigma_ladder_matches_reference(golden_dir):
+    """Host logic of the product's ARVSampler (no kernels): the staircase of per-split noise
+    levels equals the reference's (reference diffusion.py:213-221), value for value."""
+    import torch.nn as nn
+    from audio_diffusion_pytorch_b200.diffusion import ARVSampler
+    g = load(golden_dir, "tiny_autoregressive.npz")
+    s = ARVSampler(net=nn.Linear(1, 1), in_channels=2, length=4096, num_splits=4)
+    lad = s.get_sigmas_ladder(num_items=2, num_steps_per_split=3)
+    assert lad.shape == (4, 2, 1, 4096)
+    assert torch.equal(lad[:, 0, 0], t(g["ladder3"])) and torch.equal(lad[:, 1, 0], t(g["ladder3"]))

@@ -403,3 +403,35 @@ def test_autoencoder_trains_encoder_through_injected_context(oracle_port):
     e = float((got.cpu() - want).norm() / want.norm())
     print(f"encoder conv.weight.grad rel-L2 {e:.3e}")
     assert e < GRAD_TOL
+
+
+def test_autoregressive_loss_and_gradients(oracle_port):
+    """DiffusionAR.forward (reference models.py:227-250, diffusion.py:98-130): a
+    use_modulation=False net -- no ModulationItems, SkipCat merges (conv1x1 over
+    cat([skip * 2^-0.5, y])), the level-0 merge folded into the stem kernels -- under the
+    per-split-sigma loss; every parameter gradient against autograd through the CPU oracle.
+    Level 1 (8-channel output) exercises the paired-position merge GEMMs, level 2 the plain ones."""
+    import audio_diffusion_pytorch_b200 as adp
+    cfg = dict(ATT, in_channels=2, length=4096, num_splits=4)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionARPort(**cfg)
+    model = adp.DiffusionAR(net_t=adp.UNetV0, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    audio = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(25))
+    for call in range(3):                    # eager, capture, replay
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(92)
+        loss = model(audio.to(DEV))
+        loss.backward()
+    torch.manual_seed(92)                    # the draws the CUDA run consumed, replayed for the oracle
+    per_split = torch.rand((2, 1, 4), device=DEV).cpu()
+    noise = torch.randn(2, 2, 4096, device=DEV).cpu()
+    sig = per_split.repeat_interleave(1024, dim=2)
+    a, b = torch.cos(sig * math.pi / 2), torch.sin(sig * math.pi / 2)
+    loss_ref = F.mse_loss(ref.net(torch.cat([a * audio + b * noise, sig], dim=1)), a * noise - b * audio)
+    loss_ref.backward()
+    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
+    print(f"DiffusionAR loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < GRAD_TOL and cos > 1 - 1e-3
