@@ -39,6 +39,20 @@ class DiffusionModel(nn.Module):
     def sample(self, *args, **kwargs) -> Tensor:
         return self.sampler(*args, **kwargs)
 
+    def load_reference_state_dict(self, state_dict) -> None:
+        """Takes over a checkpoint of the REFERENCE model class built with the same kwargs
+        (`ref_model.state_dict()`): the U-Net tensors (`net.*`; the copies under `diffusion.net.*` /
+        `sampler.net.*` are the same tensors) are matched by position (B200UNet.load_reference_state_dict),
+        everything else (`to_flat`, `to_spectrogram`, a DiffusionAE `encoder`, ...) by name -- those
+        attributes carry the reference's names."""
+        shared = ("net.", "diffusion.net.", "sampler.net.")
+        self.net.load_reference_state_dict(state_dict, prefix="net.")
+        rest = {k: v for k, v in state_dict.items() if not k.startswith(shared)}
+        result = self.load_state_dict(rest, strict=False)
+        assert not result.unexpected_keys, f"unexpected keys {result.unexpected_keys}"
+        missing = [k for k in result.missing_keys if not k.startswith(shared)]
+        assert not missing, f"missing keys {missing}"
+
 
 class EncoderBase(nn.Module, ABC):
     """What DiffusionAE needs from an encoder: `out_channels`, `downsample_factor` and

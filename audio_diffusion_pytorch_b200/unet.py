@@ -269,6 +269,32 @@ class B200UNet(nn.Module):
             assert s.shape == d.shape, f"shape mismatch {tuple(s.shape)} vs {tuple(d.shape)}"
             d.copy_(s)
 
+    @torch.no_grad()
+    def load_reference_state_dict(self, state_dict, prefix: str = "") -> None:
+        """Loads the U-Net part of a reference checkpoint (`torch.save(model.state_dict())` of a
+        reference model built with the same kwargs) without depending on a_unet's module NAMES:
+        the keys under `prefix` are taken in checkpoint order, which is a_unet's registration
+        order = this tree's parameter order, except that the time MLP's Linear is listed twice
+        (a_unet repeats one module object inside a Sequential; both entries hold the same tensor).
+        Shapes are checked entry by entry."""
+        entries = [(k, v) for k, v in state_dict.items() if k.startswith(prefix)]
+        mine = []
+        for name, p in self.named_parameters():
+            mine.append((name, p))
+            if name == "time.mlp.bias":
+                mine += mine[-2:]
+        assert len(entries) == len(mine), \
+            f"checkpoint has {len(entries)} tensors under '{prefix}', this net expects {len(mine)}"
+        seen = {}
+        for (key, src), (name, dst) in zip(entries, mine):
+            assert tuple(src.shape) == tuple(dst.shape), \
+                f"{key}: shape {tuple(src.shape)} does not match {name} {tuple(dst.shape)}"
+            if name in seen:
+                assert torch.equal(src, seen[name]), f"{key}: repeated module entries differ"
+                continue
+            seen[name] = src
+            dst.copy_(src)
+
     def _version(self) -> int:
         return sum(p._version for p in self.parameters())
 

@@ -134,6 +134,42 @@ def test_model_classes_take_over_reference_parameters(oracle_port):
         assert voc.state_dict()[key].shape == vref.state_dict()[key].shape
 
 
+def test_reference_checkpoints_load_by_position(oracle_port, tmp_path):
+    """`model.load_reference_state_dict(torch.load(ckpt))`: a state_dict saved from the reference
+    model classes (a_unet key names, the shared net listed under three prefixes, the time MLP's
+    Linear listed twice) is taken over without knowing a_unet's module names -- text-conditional
+    net, vocoder (own layers by name), autoregressive (SkipCat) and autoencoder (user encoder)."""
+    import audio_diffusion_pytorch_b200 as adp
+    tiny = dict(channels=[8, 32, 64], factors=[1, 4, 4], items=[1, 2, 2])
+    text = dict(tiny, in_channels=2, attentions=[0, 0, 1], cross_attentions=[0, 1, 1], attention_heads=2,
+                attention_features=64, use_embedding_cfg=True, embedding_max_length=8, embedding_features=32)
+    voc_kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, **tiny)
+    ar_kw = dict(tiny, in_channels=2, length=1024, num_splits=4)
+    ae_kw = dict(tiny, in_channels=2, inject_depth=2)
+    pairs = [
+        (adp.DiffusionModel(net_t=adp.UNetV0, **text), oracle_port.DiffusionModelPort(**text)),
+        (adp.DiffusionVocoder(net_t=adp.UNetV0, **voc_kw), oracle_port.DiffusionVocoderPort(**voc_kw)),
+        (adp.DiffusionAR(net_t=adp.UNetV0, **ar_kw), oracle_port.DiffusionARPort(**ar_kw)),
+        (adp.DiffusionAE(net_t=adp.UNetV0, encoder=oracle_port.ToyEncoder(), **ae_kw),
+         oracle_port.DiffusionAEPort(encoder=oracle_port.ToyEncoder(), **ae_kw)),
+    ]
+    for i, (ours, ref) in enumerate(pairs):
+        path = tmp_path / f"ref{i}.pt"
+        torch.save(ref.state_dict(), path)
+        ckpt = torch.load(path)
+        assert not any(torch.equal(a, b) for a, b in zip(ours.net.parameters(), ref.net.parameters())
+                       if a.numel() > 64 and a.std() > 0)
+        ours.load_reference_state_dict(ckpt)
+        for a, b in zip(ours.net.parameters(), ref.net.parameters()):
+            assert torch.equal(a, b)
+        for key, val in ref.state_dict().items():
+            if not key.startswith(("net.", "diffusion.", "sampler.")):
+                assert torch.equal(ours.state_dict()[key], val), key
+    # a checkpoint of a different architecture is refused, not half-loaded
+    with pytest.raises(AssertionError):
+        pairs[0][0].load_reference_state_dict(pairs[2][1].state_dict())
+
+
 def test_upsampler_and_vocoder_conditioning_paths(oracle_port):
     """Host-side halves of DiffusionUpsampler / DiffusionVocoder (everything before the net)."""
     import audio_diffusion_pytorch_b200 as adp
