@@ -110,6 +110,11 @@ def lib() -> C.CDLL:
         "adp_sampler_step": [vp, vp, vp, vp, C.c_int64, vp],
         "adp_inpaint_blend": [vp, vp, vp, vp, vp, C.c_int64, vp],
         "adp_arv_step": [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
+        "adp_resample": [vp, vp, vp] + [C.c_int] * 7 + [vp],
+        "adp_resample_adjoint": [vp, vp, vp] + [C.c_int] * 7 + [vp],
+        "adp_mel_spectrogram": [vp] * 5 + [C.c_int] * 8 + [vp],
+        "adp_to_flat": [vp, vp, vp] + [C.c_int] * 7 + [vp],
+        "adp_to_flat_bwd": [vp] * 5 + [C.c_int] * 7 + [vp],
         "adp_step_select": [vp, vp, vp, vp, vp, C.c_int64, vp],
         "adp_step_advance": [vp, vp],
         "adp_silu_bf16": [vp, vp, C.c_int64, vp],
@@ -145,4 +150,5 @@ EXPORTS = ["adp_version", "adp_last_error", "adp_device_check", "adp_conv_gemm",
            "adp_sampler_step", "adp_silu_bf16", "adp_debug_set", "adp_wgrad", "adp_gn_silu_bwd",
            "adp_gn_bwd_apply", "adp_ln_film_bwd", "adp_colsum", "adp_skip_gate",
            "adp_skip_gate_bwd", "adp_cond_bwd", "adp_narrow_conv_bwd", "adp_stem_out_bwd",
-           "adp_stem_in_bwd", "adp_attention_bwd", "adp_ln_fold_bwd", "adp_inpaint_blend", "adp_arv_step", "adp_step_select", "adp_step_advance"]
+           "adp_stem_in_bwd", "adp_attention_bwd", "adp_ln_fold_bwd", "adp_inpaint_blend", "adp_arv_step", "adp_resample", "adp_resample_adjoint",
+           "adp_mel_spectrogram", "adp_to_flat", "adp_to_flat_bwd", "adp_step_select", "adp_step_advance"]

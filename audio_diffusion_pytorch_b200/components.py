@@ -51,8 +51,40 @@ class MelSpectrogram(nn.Module):
         self.to_mel_scale = transforms.MelScale(
             n_mels=n_mel_channels, n_stft=n_fft // 2 + 1, sample_rate=sample_rate)
 
+    def _kernel_tables(self, device):
+        """Window padded to n_fft (torch.stft centres a shorter window) and, per mel filter, the
+        bin range [lo, hi) it is non-zero on (a triangle): inputs of adp_mel_spectrogram."""
+        cached = getattr(self, "_tables", None)
+        stamp = (device, self.to_spectrogram.window._version, self.to_mel_scale.fb._version)
+        if cached is None or cached[3] != stamp:
+            n_fft = self.to_spectrogram.n_fft
+            win = self.to_spectrogram.window.to(device=device, dtype=torch.float32)
+            left = (n_fft - win.numel()) // 2
+            window = F.pad(win, (left, n_fft - win.numel() - left)).contiguous()
+            fb = self.to_mel_scale.fb.to(device=device, dtype=torch.float32).contiguous()
+            nz = fb != 0
+            bins = torch.arange(fb.shape[0], device=device)[:, None]
+            lo = torch.where(nz, bins, fb.shape[0]).amin(0)
+            hi = torch.where(nz, bins + 1, 0).amax(0)
+            band = torch.stack([torch.minimum(lo, hi), hi], dim=1).to(torch.int32).contiguous()
+            cached = self._tables = (window, fb, band, stamp)
+        return cached[:3]
+
     def forward(self, waveform: Tensor) -> Tensor:
         lead, t = waveform.shape[:-1], waveform.shape[-1]
+        if waveform.is_cuda and not (torch.is_grad_enabled() and waveform.requires_grad):
+            # one kernel: framing, window, FFT, magnitude, mel filters (+ log); autograd through
+            # the STFT (a waveform that requires grad) keeps the tensor-op route below
+            from . import ops
+            window, fb, band = self._kernel_tables(waveform.device)
+            mel = ops.mel_spectrogram(waveform.reshape(-1, t).float().contiguous(), window, fb, band,
+                                      self.to_spectrogram.n_fft, self.hop_length, self.padding,
+                                      apply_log=self.normalize_log and not self.normalize)
+            if self.normalize:
+                mel = 2 * torch.pow(mel / torch.max(mel), 0.25) - 1
+                if self.normalize_log:
+                    mel = torch.log(torch.clamp(mel, min=1e-5))
+            return mel.reshape(*lead, *mel.shape[-2:]).to(waveform.dtype)
         flat = F.pad(waveform.reshape(-1, t), [self.padding] * 2, mode="reflect")
         mel = self.to_mel_scale(torch.abs(self.to_spectrogram(flat)))
         if self.normalize:

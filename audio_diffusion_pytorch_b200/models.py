@@ -152,6 +152,28 @@ class DiffusionUpsampler(DiffusionModel):
         return super().sample(start, append_channels=guide, **kwargs)
 
 
+class _ToFlat(torch.autograd.Function):
+    """DiffusionVocoder.to_flat = ConvTranspose1d(mel -> 1, bias-free) as the adp_to_flat kernel;
+    backward = adp_to_flat_bwd (weight gradient: the only trainable part of the front-end)."""
+
+    @staticmethod
+    def forward(ctx, spec: Tensor, weight: Tensor, hop: int, pad: int) -> Tensor:
+        from . import ops
+        spec, w = spec.contiguous(), weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+        ctx.save_for_backward(spec, w)
+        ctx.geom = (hop, pad, weight.shape, weight.dtype)
+        return ops.to_flat(spec, w, hop, pad)
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        from . import ops
+        spec, w = ctx.saved_tensors
+        hop, pad, w_shape, w_dtype = ctx.geom
+        dspec, dw = ops.to_flat_bwd(spec, w, dout.float().contiguous(), hop, pad,
+                                    need_dspec=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1])
+        return dspec, (None if dw is None else dw.reshape(w_shape).to(w_dtype)), None, None
+
+
 class DiffusionVocoder(DiffusionModel):
     """Mel spectrogram -> waveform.  Every audio channel becomes its own batch row; a bias-free
     transposed convolution (`to_flat`) stretches the spectrogram to one waveform-rate channel
@@ -172,7 +194,12 @@ class DiffusionVocoder(DiffusionModel):
     def _unroll(self, spectrogram: Tensor) -> Tuple[Tensor, torch.Size]:
         """[..., mel, frames] -> ([rows, 1, samples], leading shape)."""
         lead = spectrogram.shape[:-2]
-        return self.to_flat(spectrogram.reshape(-1, *spectrogram.shape[-2:])), lead
+        spec = spectrogram.reshape(-1, *spectrogram.shape[-2:])
+        if spec.is_cuda:         # adp_to_flat (+ its weight / input gradients)
+            flat = _ToFlat.apply(spec.float(), self.to_flat.weight, self.to_flat.stride[0],
+                                 self.to_flat.padding[0])
+            return flat[:, None, :].to(spectrogram.dtype), lead
+        return self.to_flat(spec), lead
 
     def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
         guide, _ = self._unroll(self.to_spectrogram(x))

@@ -348,6 +348,69 @@ def arv_step(chan: Tensor, v: Tensor, sig_next: Tensor) -> Tensor:
     return chan
 
 
+# ----------------------------------------------------------------------------- front-ends
+def fir_resample(x: Tensor, bank: Tensor, factor_in: int, factor_out: int, half: int, t_out: int,
+                 adjoint_of: Optional[int] = None) -> Tensor:
+    """x fp32 [rows, t] -> [rows, t_out] through the polyphase bank [factor_out, taps]
+    (adp_resample); with adjoint_of = t the transposed map [rows, t_out] -> [rows, t]."""
+    rows = x.shape[0]
+    taps = bank.shape[1]
+    if adjoint_of is None:
+        t = x.shape[1]
+        y = torch.empty(rows, t_out, device=x.device, dtype=torch.float32)
+        _launch(lambda: _lib.lib().adp_resample(x.data_ptr(), bank.data_ptr(), y.data_ptr(), rows, t, t_out,
+                                                factor_in, factor_out, taps, half, _stream()),
+                "adp_resample", lambda: (f"resample[{factor_in}->{factor_out}]", 2.0 * rows * t_out * taps,
+                                         _nb(x, y)))
+        return y
+    t = adjoint_of
+    dx = torch.empty(rows, t, device=x.device, dtype=torch.float32)
+    _launch(lambda: _lib.lib().adp_resample_adjoint(x.data_ptr(), bank.data_ptr(), dx.data_ptr(), rows, t,
+                                                    t_out, factor_in, factor_out, taps, half, _stream()),
+            "adp_resample_adjoint", lambda: (f"resample_adjoint[{factor_in}->{factor_out}]",
+                                             2.0 * rows * t_out * taps, _nb(x, dx)))
+    return dx
+
+
+def mel_spectrogram(wave: Tensor, window: Tensor, fb: Tensor, band: Tensor, n_fft: int, hop: int,
+                    pad: int, apply_log: bool) -> Tensor:
+    """wave fp32 [rows, t] -> mel fp32 [rows, n_mels, frames] (adp_mel_spectrogram)."""
+    rows, t = wave.shape
+    n_mels = fb.shape[1]
+    frames = 1 + (t + 2 * pad - n_fft) // hop
+    mel = torch.empty(rows, n_mels, frames, device=wave.device, dtype=torch.float32)
+    _launch(lambda: _lib.lib().adp_mel_spectrogram(wave.data_ptr(), window.data_ptr(), fb.data_ptr(),
+                                                   band.data_ptr(), mel.data_ptr(), rows, t, n_fft, hop, pad,
+                                                   frames, n_mels, 1 if apply_log else 0, _stream()),
+            "adp_mel_spectrogram", lambda: (f"mel_spectrogram[n_fft={n_fft}]", 0, _nb(wave, mel)))
+    return mel
+
+
+def to_flat(spec: Tensor, w: Tensor, hop: int, pad: int) -> Tensor:
+    """spec fp32 [B, C, frames], w fp32 [C, win] -> [B, t_out] (adp_to_flat)."""
+    B, Cc, frames = spec.shape
+    win = w.shape[1]
+    t_out = (frames - 1) * hop - 2 * pad + win
+    out = torch.empty(B, t_out, device=spec.device, dtype=torch.float32)
+    _launch(lambda: _lib.lib().adp_to_flat(spec.data_ptr(), w.data_ptr(), out.data_ptr(), B, Cc, frames, win,
+                                           hop, pad, t_out, _stream()),
+            "adp_to_flat", lambda: ("to_flat", 2.0 * B * t_out * Cc * (win // hop), _nb(spec, out)))
+    return out
+
+
+def to_flat_bwd(spec: Tensor, w: Tensor, dout: Tensor, hop: int, pad: int, need_dspec: bool,
+                need_dw: bool):
+    B, Cc, frames = spec.shape
+    win = w.shape[1]
+    t_out = dout.shape[1]
+    dspec = torch.empty_like(spec) if need_dspec else None
+    dw = torch.zeros_like(w) if need_dw else None
+    _launch(lambda: _lib.lib().adp_to_flat_bwd(spec.data_ptr(), w.data_ptr(), dout.data_ptr(), _p(dspec),
+                                               _p(dw), B, Cc, frames, win, hop, pad, t_out, _stream()),
+            "adp_to_flat_bwd", lambda: ("to_flat_bwd", 4.0 * B * Cc * frames * win, _nb(spec, dout)))
+    return dspec, dw
+
+
 # ----------------------------------------------------------------------------- backward
 def pack_conv_dgrad(w: Tensor) -> Tensor:
     """Weights of the data-gradient conv: dA[t] = sum_j dOut[t + o_j] @ Wt_j with the taps

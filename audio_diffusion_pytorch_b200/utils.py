@@ -64,10 +64,35 @@ def _polyphase_bank(factor_in: int, factor_out: int, rolloff: float, zeros: int,
     return sinc * (hann * (cutoff / factor_in)), half
 
 
+class _FirResample(torch.autograd.Function):
+    """The polyphase FIR as one kernel (adp_resample); backward = its transpose (adp_resample_adjoint)."""
+
+    @staticmethod
+    def forward(ctx, rows: Tensor, bank: Tensor, factor_in: int, factor_out: int, half: int, t_out: int):
+        from . import ops
+        ctx.bank, ctx.geom = bank, (factor_in, factor_out, half, t_out, rows.shape[1])
+        return ops.fir_resample(rows.contiguous(), bank, factor_in, factor_out, half, t_out)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        from . import ops
+        fi, fo, half, t_out, t = ctx.geom
+        return ops.fir_resample(dy.contiguous(), ctx.bank, fi, fo, half, t_out, adjoint_of=t), None, None, \
+            None, None, None
+
+
 def resample(waveforms: Tensor, factor_in: int, factor_out: int, rolloff: float = 0.99,
              lowpass_filter_width: int = 6) -> Tensor:
-    """[b, c, t] -> [b, c, t * factor_out / factor_in]."""
+    """[b, c, t] -> [b, c, t * factor_out / factor_in].  CUDA tensors go through the adp_resample
+    kernel (one pass, no padded copy, no [rows, phases, frames] intermediate); host tensors through
+    the same filter bank as a strided convolution."""
     b, c, t = waveforms.shape
+    if waveforms.is_cuda:
+        bank, half = _polyphase_bank(int(factor_in), int(factor_out), float(rolloff),
+                                     int(lowpass_filter_width), torch.float32, str(waveforms.device))
+        out = _FirResample.apply(waveforms.reshape(b * c, t).float(), bank[:, 0].contiguous(),
+                                 int(factor_in), int(factor_out), half, int(factor_out * t / factor_in))
+        return out.reshape(b, c, -1).to(waveforms.dtype)
     bank, half = _polyphase_bank(int(factor_in), int(factor_out), float(rolloff),
                                  int(lowpass_filter_width), waveforms.dtype, str(waveforms.device))
     rows = F.pad(waveforms.reshape(b * c, t), (half, half + factor_in))

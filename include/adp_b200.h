@@ -245,6 +245,37 @@ int adp_arv_step(float* chan, const float* v, const float* sig_next, int B, int 
                  adp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Conditioning front-ends of the model wrappers (fp32, once per call, outside the step loop).
+ *
+ * adp_resample: polyphase windowed-sinc rate change by factor_out / factor_in (reference
+ * utils.py:82-117 `resample`, used by DiffusionUpsampler.reupsample / .sample, models.py:141-165).
+ * x [rows, t], bank [factor_out, taps] (taps = 2*half + factor_in, the Hann-windowed sinc
+ * phases), y [rows, t_out]:  y[r, i*factor_out + p] = sum_k xpad[r, i*factor_in + k] * bank[p, k],
+ * xpad = x shifted by `half` with zeros outside.  adp_resample_adjoint is its transpose
+ * (dx from dy), the backward of the same op. */
+int adp_resample(const float* x, const float* bank, float* y, int rows, int t, int t_out,
+                 int factor_in, int factor_out, int taps, int half, adp_stream_t stream);
+int adp_resample_adjoint(const float* dy, const float* bank, float* dx, int rows, int t, int t_out,
+                         int factor_in, int factor_out, int taps, int half, adp_stream_t stream);
+
+/* MelSpectrogram (reference components.py:188-236): reflect padding by `pad`, frames of n_fft
+ * samples every `hop` (center=False), window [n_fft], |rFFT|, mel filterbank fb [n_fft/2+1, n_mels]
+ * whose column m is non-zero on bins [band[2m], band[2m+1]); apply_log: log(max(mel, 1e-5)).
+ * wave [rows, t] -> mel [rows, n_mels, frames].  n_fft: a power of two in [32, 4096]. */
+int adp_mel_spectrogram(const float* wave, const float* window, const float* fb, const int32_t* band,
+                        float* mel, int rows, int t, int n_fft, int hop, int pad, int frames,
+                        int n_mels, int apply_log, adp_stream_t stream);
+
+/* DiffusionVocoder.to_flat (reference models.py:194-201): ConvTranspose1d(C -> 1, kernel win,
+ * stride hop, padding pad, bias-free).  spec [B, C, frames], w [C, win], out [B, t_out] with
+ * t_out = (frames-1)*hop - 2*pad + win.  adp_to_flat_bwd: dspec [B, C, frames] (may be NULL) and
+ * dw [C, win] (may be NULL; ACCUMULATES, zeroed by the caller) from dout [B, t_out]. */
+int adp_to_flat(const float* spec, const float* w, float* out, int B, int C, int frames, int win,
+                int hop, int pad, int t_out, adp_stream_t stream);
+int adp_to_flat_bwd(const float* spec, const float* w, const float* dout, float* dspec, float* dw,
+                    int B, int C, int frames, int win, int hop, int pad, int t_out, adp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Backward (training) entry points: VDiffusion loss.backward() through UNetV0
  * (reference diffusion.py:82-95 + autograd over the a_unet blocks).  Data gradients are
  * channels-last bf16; parameter gradients accumulate in fp32 buffers zeroed by the caller.
