@@ -68,17 +68,36 @@ def _worker(rank, world, port, out_dir):
     s_full = model.sample(noise, num_steps=3)
     s_shard = parallel.sample_sharded(model, noise, 3)
     rel_s = float((s_shard - s_full).norm() / s_full.norm())
+    # use_modulation=False net (DiffusionAR): no conditioning projection to gather, level-0 merge
+    # gradients unfolded from the all-reduced folded ones
+    torch.manual_seed(1)
+    ar = adp.DiffusionAR(net_t=adp.UNetV0, length=4096, num_splits=4, **CFG).to(dev)
+    chan = torch.cat([x, sigma.view(4, 1, 1).expand(4, 1, 4096)], dim=1)
+    ar.zero_grad()
+    torch.nn.functional.mse_loss(ar.net(chan), noise).backward()
+    full_ar = [p.grad.clone() for p in ar.parameters()]
+    odp_ar = parallel.OverlappedDataParallel(ar, bucket_mb=0.05)
+    rel_ar = 0.0
+    for _ in range(3):
+        ar.zero_grad()
+        torch.nn.functional.mse_loss(ar.net(chan[lo:hi]), noise[lo:hi]).backward()
+        odp_ar.finish_gradient_sync()
+        num = sum(float((p.grad - f).double().norm() ** 2) for p, f in zip(ar.parameters(), full_ar))
+        den_ar = sum(float(f.double().norm() ** 2) for f in full_ar)
+        rel_ar = max(rel_ar, (num / den_ar) ** 0.5)
     if rank == 0:
-        open(os.path.join(out_dir, "result"), "w").write(f"{rel} {grads_ok} {same} {rel_s} {rel_o} {n_seg}")
+        open(os.path.join(out_dir, "result"), "w").write(
+            f"{rel} {grads_ok} {same} {rel_s} {rel_o} {n_seg} {rel_ar}")
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_gradients_and_sampling(tmp_path):
     mp.spawn(_worker, args=(2, 29600 + os.getpid() % 2000, str(tmp_path)), nprocs=2, join=True)
-    rel, grads_ok, same, rel_s, rel_o, n_seg = open(tmp_path / "result").read().split()
+    rel, grads_ok, same, rel_s, rel_o, n_seg, rel_ar = open(tmp_path / "result").read().split()
     print("DP gradient rel-L2 vs full batch:", rel, "DDP grads finite:", grads_ok,
           "identical across ranks:", same, "sharded sampling rel-L2:", rel_s,
           "overlapped all-reduce rel-L2:", rel_o, "backward graph segments:", n_seg)
     assert float(rel) < 2e-2 and grads_ok == "True" and same == "True" and float(rel_s) < 2e-3
-    assert float(rel_o) < 2e-2 and int(n_seg) >= 2
+    print("DiffusionAR overlapped all-reduce rel-L2:", rel_ar)
+    assert float(rel_o) < 2e-2 and int(n_seg) >= 2 and float(rel_ar) < 2e-2

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu_info.txt 2>&1
 status=0
-files=${@:-tests/test_bwd_ops_gpu.py tests/test_train_gpu.py tests/test_net_gpu.py tests/test_ops_gpu.py tests/test_ddp_gpu.py}
+files=${@:-tests/test_bwd_ops_gpu.py tests/test_train_gpu.py tests/test_net_gpu.py tests/test_ops_gpu.py tests/test_frontend_gpu.py tests/test_ddp_gpu.py}
 for f in $files; do
   name=$(basename "$f" .py)
   timeout 1200 python -m pytest "$f" -m gpu -q --no-header -p no:cacheprovider -s \
