@@ -94,9 +94,29 @@ def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+# storage type of packed GEMM operands: bf16 for the tensor-core path, fp32 while B200UNet packs
+# for its fp32 verification mode (pack_dtype() context)
+_PACK_DTYPE = [torch.bfloat16]
+
+
+class pack_dtype:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        _PACK_DTYPE.append(self.dtype)
+
+    def __exit__(self, *exc):
+        _PACK_DTYPE.pop()
+
+
+def packed_dtype():
+    return _PACK_DTYPE[-1]
+
+
 def _pad_rows(w2d: Tensor, n_pad: int) -> Tensor:
-    out = torch.zeros(n_pad, w2d.shape[1], dtype=torch.bfloat16, device=w2d.device)
-    out[: w2d.shape[0]] = w2d.to(torch.bfloat16)
+    out = torch.zeros(n_pad, w2d.shape[1], dtype=_PACK_DTYPE[-1], device=w2d.device)
+    out[: w2d.shape[0]] = w2d.to(_PACK_DTYPE[-1])
     return out.contiguous()
 
 
@@ -129,7 +149,7 @@ def pack_upsample_conv(w: Tensor, f: int) -> Tensor:
             out[p, :co, :ci], out[p, :co, ci:] = w0 + w1, w2
         else:
             out[p, :co, :ci] = w0 + w1 + w2
-    return out.reshape(f * n_pad, 2 * ci).to(torch.bfloat16).contiguous()
+    return out.reshape(f * n_pad, 2 * ci).to(_PACK_DTYPE[-1]).contiguous()
 
 
 # ---------------------------------------------------------------------------------- ops
@@ -166,6 +186,15 @@ def conv_gemm(a: Tensor, w: Tensor, out: Tensor, *, c_in: int, n_valid: int,
             + rows * phases * n_valid * out.element_size() * (2 if residual is not None else 1)
         return f"conv_gemm[{kind} M={rows} K={c_in} N={n_valid}x{phases}]", flops, nbytes
 
+    if a.dtype == torch.float32:       # fp32 verification mode (csrc/verify_f32.cu)
+        assert w.dtype == torch.float32 and out.dtype == torch.float32 and gn is None
+        assert residual is None or residual.dtype == torch.float32
+        args.stats, args.out_fp32 = None, 0
+        _launch(lambda: _lib.lib().adp_f32_conv_gemm(C.byref(args), _stream()), "adp_f32_conv_gemm", meta)
+        if stats is not None:
+            assert out.shape[-1] == phases * n_valid, "statistics need a dense output"
+            gn_stats(out.reshape(B, -1, n_valid), stats, groups)
+        return out
     _launch(lambda: _lib.lib().adp_conv_gemm(C.byref(args), _stream()), "adp_conv_gemm", meta)
     return out
 
@@ -173,6 +202,11 @@ def conv_gemm(a: Tensor, w: Tensor, out: Tensor, *, c_in: int, n_valid: int,
 def gn_silu(x: Tensor, y: Tensor, stats: Tensor, gamma: Tensor, beta: Tensor, groups: int,
             eps: float = 1e-5) -> Tensor:
     B, T, Cc = x.shape
+    if x.dtype == torch.float32:
+        _launch(lambda: _lib.lib().adp_f32_gn_silu(x.data_ptr(), y.data_ptr(), stats.data_ptr(), gamma.data_ptr(),
+                                                   beta.data_ptr(), B, T, Cc, groups, eps, _stream()),
+                "adp_f32_gn_silu", lambda: (f"f32_gn_silu[M={B * T} C={Cc}]", 0, _nb(x, y)))
+        return y
     _launch(lambda: _lib.lib().adp_gn_silu(x.data_ptr(), y.data_ptr(), stats.data_ptr(),
                                            gamma.data_ptr(), beta.data_ptr(), B, T, Cc, groups,
                                            eps, _stream()), "adp_gn_silu",
@@ -182,6 +216,11 @@ def gn_silu(x: Tensor, y: Tensor, stats: Tensor, gamma: Tensor, beta: Tensor, gr
 
 def gn_stats(x: Tensor, stats: Tensor, groups: int) -> Tensor:
     B, T, Cc = x.shape
+    if x.dtype == torch.float32:
+        assert x.is_contiguous()
+        _launch(lambda: _lib.lib().adp_f32_gn_stats(x.data_ptr(), stats.data_ptr(), B, T, Cc, groups, _stream()),
+                "adp_f32_gn_stats", lambda: (f"f32_gn_stats[M={B * T} C={Cc}]", 0, _nb(x)))
+        return stats
     _launch(lambda: _lib.lib().adp_gn_stats(x.data_ptr(), stats.data_ptr(), B, T, Cc, groups,
                                             _stream()), "adp_gn_stats",
             lambda: (f"gn_stats[M={B * T} C={Cc}]", 0, _nb(x)))
@@ -193,6 +232,13 @@ def ln_film(x: Tensor, y: Tensor, scale_shift: Optional[Tensor] = None, ss_strid
             y2: Optional[Tensor] = None, eps2: float = 1e-5) -> Tensor:
     """y = LN(x)*(1+scale)+shift; with y2 also y2 = LN(y; eps2) in the same pass."""
     B, T, Cc = x.shape
+    if x.dtype == torch.float32:
+        _launch(lambda: _lib.lib().adp_f32_ln_film(x.data_ptr(), y.data_ptr(), _p(y2), _p(scale_shift), ss_stride,
+                                                   B, T, Cc, eps, eps2, _stream()),
+                "adp_f32_ln_film", lambda: (f"f32_ln_film[M={B * T} C={Cc}]", 0, _nb(x, y, y2)))
+        if stats_out is not None:
+            gn_stats(y, stats_out, groups)
+        return y
     if y2 is None:
         _launch(lambda: _lib.lib().adp_ln_film(x.data_ptr(), y.data_ptr(), _p(scale_shift), ss_stride,
                                                _p(stats_out), B, T, Cc, groups, eps, _stream()),
@@ -211,6 +257,14 @@ def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: flo
     lse: optional fp32 [B, heads, Tq] output (kept for attention_bwd)."""
     B, Tq = q.shape[0], q.shape[1]
     Tk = k.shape[1]
+    if q.dtype == torch.float32:
+        assert lse is None, "the fp32 verification mode covers inference only"
+        _launch(lambda: _lib.lib().adp_f32_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B,
+                                                     heads, Tq, Tk, q.stride(1), k.stride(1), v.stride(1),
+                                                     o.stride(1), scale, _stream()),
+                "adp_f32_attention", lambda: (f"f32_attention[B={B} H={heads} Tq={Tq} Tk={Tk}]",
+                                              4.0 * B * heads * Tq * Tk * 64, 0))
+        return o
     _launch(lambda: _lib.lib().adp_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
                                              B, heads, Tq, Tk, q.stride(1), k.stride(1),
                                              v.stride(1), o.stride(1), scale, _p(lse), _stream()),
@@ -222,6 +276,13 @@ def attention(q: Tensor, k: Tensor, v: Tensor, o: Tensor, heads: int, scale: flo
 
 def skinny_linear(x: Tensor, w: Tensor, bias: Optional[Tensor], y: Tensor, K: int, N: int,
                   in_act: int = ACT_NONE, out_act: int = ACT_NONE) -> Tensor:
+    if w.dtype == torch.float32:
+        _launch(lambda: _lib.lib().adp_f32_linear(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(), x.shape[0],
+                                                  K, N, x.stride(0), w.stride(0), y.stride(0), in_act, out_act,
+                                                  _stream()),
+                "adp_f32_linear", lambda: (f"f32_linear[B={x.shape[0]} K={K} N={N}]", 2.0 * x.shape[0] * K * N,
+                                           _nb(w)))
+        return y
     _launch(lambda: _lib.lib().adp_skinny_linear(x.data_ptr(), w.data_ptr(), _p(bias), y.data_ptr(),
                                                  x.shape[0], K, N, x.stride(0), w.stride(0),
                                                  y.stride(0), in_act, out_act, _stream()),
@@ -239,6 +300,10 @@ def time_features(sigma: Tensor, freqs: Tensor, out: Tensor) -> Tensor:
 
 
 def silu_bf16(x: Tensor, y: Tensor) -> Tensor:
+    if y.dtype == torch.float32:
+        _launch(lambda: _lib.lib().adp_f32_silu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()),
+                "adp_f32_silu", lambda: ("f32_silu", 0, _nb(x, y)))
+        return y
     _launch(lambda: _lib.lib().adp_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()),
             "adp_silu_bf16", lambda: ("silu_bf16", 0, _nb(x, y)))
     return y
@@ -254,6 +319,14 @@ def stem_in(x: Tensor, w: Tensor, bias: Optional[Tensor], out: Tensor, f: int, *
     a.B, a.cx, a.T = x.shape
     a.ca = 0 if append is None else append.shape[1]
     a.c0, a.f, a.groups = w.shape[0], f, groups
+    if out.dtype == torch.float32:
+        assert noise is None
+        a.stats = None
+        _launch(lambda: _lib.lib().adp_f32_stem_in(C.byref(a), _stream()), "adp_f32_stem_in",
+                lambda: (f"f32_stem_in[B={x.shape[0]} T={x.shape[2]} c0={w.shape[0]}]", 0, _nb(x, append, out)))
+        if stats is not None:
+            gn_stats(out, stats, groups)
+        return out
     _launch(lambda: _lib.lib().adp_stem_in(C.byref(a), _stream()), "adp_stem_in",
             lambda: (f"stem_in[B={x.shape[0]} T={x.shape[2]} c0={w.shape[0]}]",
                      2.0 * out.numel() * w.shape[1] * w.shape[2], _nb(x, append, noise, out)))
@@ -278,6 +351,10 @@ def stem_out(h: Tensor, x: Tensor, w: Tensor, bias: Optional[Tensor], gate: Tens
     a.ca = 0 if append is None else append.shape[1]
     a.c0, a.co, a.f = h.shape[-1], w.shape[0], f
     a.ld_gate = gate.stride(0)
+    if h.dtype == torch.float32:
+        _launch(lambda: _lib.lib().adp_f32_stem_out(C.byref(a), _stream()), "adp_f32_stem_out",
+                lambda: (f"f32_stem_out[B={x.shape[0]} T={x.shape[2]} c0={h.shape[-1]}]", 0, _nb(h, x, v_out)))
+        return
     _launch(lambda: _lib.lib().adp_stem_out(C.byref(a), _stream()), "adp_stem_out",
             lambda: (f"stem_out[B={x.shape[0]} T={x.shape[2]} c0={h.shape[-1]}]",
                      2.0 * h.shape[0] * x.shape[2] * w.numel(),

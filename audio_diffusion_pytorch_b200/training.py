@@ -768,6 +768,9 @@ class _UNetFn(torch.autograd.Function):
     def forward(ctx, net: B200UNet, mode: str, x, noise, sigmas, append, cond, embedding, ctx_depths,
                 *rest):
         context, params = rest[:len(ctx_depths)], rest[len(ctx_depths):]
+        if net.verify_fp32:
+            raise NotImplementedError("B200UNet.verify_fp32 covers inference and sampling; run it under "
+                                      "torch.no_grad() (the differentiable program is bf16 only)")
         B, _, T = x.shape
         M = embedding.shape[1] if (embedding is not None and any(net.cross_attentions)) else 0
         need = ctx.needs_input_grad       # (net, mode, x, noise, sigmas, append, cond, embedding, ...)

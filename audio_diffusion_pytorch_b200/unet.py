@@ -115,12 +115,13 @@ class TimeParams(nn.Module):
 class _Pool:
     """Reuses activation buffers whose value is dead (better L2 residency than fresh ones)."""
 
-    def __init__(self, device, reuse: bool):
-        self.device, self.reuse = device, reuse
+    def __init__(self, device, reuse: bool, dtype=torch.bfloat16):
+        self.device, self.reuse, self.dtype = device, reuse, dtype
         self.free: Dict[Tuple, List[Tensor]] = {}
         self.total_bytes = 0
 
-    def get(self, *shape, dtype=torch.bfloat16) -> Tensor:
+    def get(self, *shape, dtype=None) -> Tensor:
+        dtype = self.dtype if dtype is None else dtype
         key = (tuple(shape), dtype)
         lst = self.free.get(key)
         if self.reuse and lst:
@@ -250,6 +251,25 @@ class B200UNet(nn.Module):
         self.cond_table_rows = 4096    # sampler: rows (steps x batch) of conditioning per pass
         self.max_table_steps = 4096    # iterations per conditioning block (alpha/beta table rows)
         self.steps_per_graph = 10      # sampling steps captured back to back in one CUDA graph
+        self._verify_fp32 = False
+
+    @property
+    def verify_fp32(self) -> bool:
+        """fp32 VERIFICATION MODE (inference and sampling): the same launch program, packed-weight
+        layouts and folds, with fp32 storage and fp32 arithmetic on the simple kernels of
+        csrc/verify_f32.cu (the fused thin-level kernels are replaced by their unfused
+        composition).  For checking the program against the reference at rtol 1e-3 / atol 1e-4;
+        ~100x slower than the tensor-core path.  Switching drops every plan and pack."""
+        return self._verify_fp32
+
+    @verify_fp32.setter
+    def verify_fp32(self, on: bool) -> None:
+        if bool(on) != self._verify_fp32:
+            self._verify_fp32 = bool(on)
+            self.invalidate()
+
+    def _act_dtype(self):
+        return torch.float32 if self._verify_fp32 else torch.bfloat16
 
     # ------------------------------------------------------------------ weights
     def levels(self) -> List[LevelParams]:
@@ -377,7 +397,12 @@ class B200UNet(nn.Module):
 
     @torch.no_grad()
     def _compute_packed(self):
+        with ops.pack_dtype(self._act_dtype()):
+            return self._compute_packed_impl()
+
+    def _compute_packed_impl(self):
         P: Dict = {}
+        pd = self._act_dtype()
         f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
         cond_w, cond_b, off = [], [], 0
 
@@ -440,7 +465,7 @@ class B200UNet(nn.Module):
 
         P["levels"] = []
         for i, lvl in enumerate(self.levels()):
-            narrow = lvl.ch == 8
+            narrow = lvl.ch == 8 and not self._verify_fp32
             L: Dict = {"down_b": f32(lvl.down.bias), "up_b": f32(lvl.up.bias)}
             if i == 0:
                 L["down_w"], L["up_w"] = f32(lvl.down.weight), f32(lvl.up.weight)
@@ -485,8 +510,8 @@ class B200UNet(nn.Module):
         if cond_w:
             w_all = torch.cat(cond_w, 0)
             n_pad = ops.round_up(n_tot, 256)
-            w_pad = torch.zeros(n_pad, w_all.shape[1], dtype=torch.bfloat16, device=w_all.device)
-            w_pad[:n_tot] = w_all.to(torch.bfloat16)
+            w_pad = torch.zeros(n_pad, w_all.shape[1], dtype=pd, device=w_all.device)
+            w_pad[:n_tot] = w_all.to(pd)
             P["cond_w"], P["cond_b"], P["cond_n"] = w_pad.contiguous(), torch.cat(cond_b).contiguous(), n_tot
         else:          # use_modulation=False: no conditioning linears at all
             P["cond_w"], P["cond_b"], P["cond_n"] = None, None, 0
@@ -494,10 +519,10 @@ class B200UNet(nn.Module):
             t = self.time
             kdim = t.to_out.weight.shape[1]
             kpad = ops.round_up(kdim, 8)
-            w_emb = torch.zeros(self.features, kpad, dtype=torch.bfloat16, device=w_all.device)
-            w_emb[:, :kdim] = t.to_out.weight.detach().to(torch.bfloat16)
+            w_emb = torch.zeros(self.features, kpad, dtype=pd, device=w_all.device)
+            w_emb[:, :kdim] = t.to_out.weight.detach().to(pd)
             P["time"] = {"freqs": f32(t.weights), "w_emb": w_emb.contiguous(), "b_emb": f32(t.to_out.bias),
-                         "w_mlp": t.mlp.weight.detach().to(torch.bfloat16).contiguous(),
+                         "w_mlp": t.mlp.weight.detach().to(pd).contiguous(),
                          "b_mlp": f32(t.mlp.bias), "kpad": kpad}
         return P
 
@@ -509,7 +534,7 @@ class B200UNet(nn.Module):
         Fm = self.features
         n_tot = P["cond_n"]
         ss_all = torch.zeros(Bh, ops.round_up(n_tot, 8), device=dev)
-        cond_bf = torch.zeros(1, Bh, Fm, dtype=torch.bfloat16, device=dev)
+        cond_bf = torch.zeros(1, Bh, Fm, dtype=self._act_dtype(), device=dev)
         fvec = torch.zeros(Bh, Fm, device=dev)
         plan.use_features_in = False
         if self.time is not None:
@@ -570,7 +595,7 @@ class B200UNet(nn.Module):
         dev = self.net.down.weight.device
         P = self.packed()
         plan = _Plan()
-        pool = _Pool(dev, reuse=True)
+        pool = _Pool(dev, reuse=True, dtype=self._act_dtype())
         G, Fm = self.groups, self.features
         levels = self.levels()
         total_f = 1
@@ -585,11 +610,11 @@ class B200UNet(nn.Module):
         plan.features_in = torch.zeros(Bh, Fm, device=dev)
         plan.v = torch.zeros(B, self.out_channels, T, device=dev)
         plan.ab = torch.zeros(4, device=dev)
-        plan.embedding = torch.zeros(Bh, M, self.embedding_features, dtype=torch.bfloat16,
-                                     device=dev) if M else None
+        adt = self._act_dtype()
+        plan.embedding = torch.zeros(Bh, M, self.embedding_features, dtype=adt, device=dev) if M else None
         plan.cfg_scale = None
         plan.ctx = {i: torch.zeros(Bh, (T // _prod(self.factors[:i + 1])), ops.round_up(c, 16),
-                                   dtype=torch.bfloat16, device=dev)
+                                   dtype=adt, device=dev)
                     for i, c in enumerate(self.context_channels) if c > 0}
         plan.en = None                       # LayerNorm(embedding), shared by all cross-attentions
         plan.pre = []                        # step-invariant launches of a sampling plan
@@ -635,10 +660,11 @@ class B200UNet(nn.Module):
         def run_items(x: Tensor, x_stats: Tensor, items_p: List[Dict], lv: LevelParams, Tl: int,
                       last_needs_stats: bool, li: int = 0) -> Tuple[Tensor, Optional[Tensor]]:
             C = lv.ch
-            narrow = C == 8
+            narrow = C == 8 and not self._verify_fp32
             # thin levels (C = 32, 64) are HBM-bound: one fused ConvBlock kernel (mid_conv.cu)
             # instead of gn_silu -> conv_gemm (-> ln_film)
-            thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 4 == 0)
+            thin = narrow or (self.fuse_thin_levels and C in (32, 64) and (C // G) % 4 == 0
+                              and not self._verify_fp32)
             for idx, ip in enumerate(items_p):
                 ss = ss_all[:, ip["ss_off"]:] if mod else None
                 has_att, has_cross, has_inj = "att" in ip, "cross" in ip, "inj" in ip
@@ -741,10 +767,10 @@ class B200UNet(nn.Module):
                         E = self.embedding_features
                         q = pool.get(Bh, Tl, mid)
                         if plan.en is None:
-                            plan.en = torch.empty(Bh, M, E, dtype=torch.bfloat16, device=dev)
+                            plan.en = torch.empty(Bh, M, E, dtype=adt, device=dev)
                             add_ctx(lambda: ops.ln_film(plan.embedding, plan.en, None, 0, None, G,
                                                         self.ATT_LN_EPS))
-                        kv = torch.empty(Bh, M, 2 * mid, dtype=torch.bfloat16, device=dev)
+                        kv = torch.empty(Bh, M, 2 * mid, dtype=adt, device=dev)
                         add_ctx(lambda kv=kv, ap=ap: ops.conv_gemm(
                             plan.en, ap["w_kv"], kv, c_in=E, n_valid=2 * mid, bias=ap["b_kv"]))
                         plan.add(lambda xn=xn, q=q, ap=ap: ops.conv_gemm(

@@ -245,6 +245,30 @@ int adp_arv_step(float* chan, const float* v, const float* sig_next, int B, int 
                  adp_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * fp32 VERIFICATION MODE (B200UNet.verify_fp32, csrc/verify_f32.cu): the inference program of the
+ * bf16 path -- same launch sequence, packed-weight layouts, folds -- with fp32 activations and
+ * weights on simple CUDA-core kernels (exact SiLU / GELU / exp), to check the program against
+ * the reference at rtol 1e-3 / atol 1e-4.  Same argument meaning as the entry point each one
+ * shadows; every activation / weight pointer is fp32; GroupNorm statistics are produced by
+ * adp_f32_gn_stats as a separate pass (args->stats, fused GroupNorm, noising and the fused loss
+ * must be unset).  ~100x slower than the tensor-core path: never used for measurement. */
+int adp_f32_conv_gemm(const adp_conv_gemm_args* args, adp_stream_t stream);
+int adp_f32_gn_stats(const float* x, double* stats, int B, int T, int C, int groups, adp_stream_t stream);
+int adp_f32_gn_silu(const float* x, float* y, const double* stats, const float* gamma, const float* beta,
+                    int B, int T, int C, int groups, float eps, adp_stream_t stream);
+/* y = LN(x; eps) * (1 + scale) + shift (scale_shift may be NULL); y2 (may be NULL) = LN(y; eps2) */
+int adp_f32_ln_film(const float* x, float* y, float* y2, const float* scale_shift, int ss_stride, int B,
+                    int T, int C, float eps, float eps2, adp_stream_t stream);
+int adp_f32_attention(const float* q, const float* k, const float* v, float* o, int B, int H, int Tq, int Tk,
+                      int ldq, int ldk, int ldv, int ldo, float scale, adp_stream_t stream);
+/* y[b,n] = act_out(sum_k act_in(x[b,k]) * w[n,k] + bias[n])  (shadows adp_skinny_linear) */
+int adp_f32_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int ldx,
+                   int ldw, int ldy, int in_act, int out_act, adp_stream_t stream);
+int adp_f32_silu(const float* x, float* y, int64_t n, adp_stream_t stream);
+int adp_f32_stem_in(const adp_stem_in_args* args, adp_stream_t stream);   /* args->out fp32 */
+int adp_f32_stem_out(const adp_stem_out_args* args, adp_stream_t stream); /* args->h fp32 */
+
+/* ---------------------------------------------------------------------------------------
  * Conditioning front-ends of the model wrappers (fp32, once per call, outside the step loop).
  *
  * adp_resample: polyphase windowed-sinc rate change by factor_out / factor_in (reference

@@ -371,3 +371,72 @@ def test_autoregressive_net_and_sampler_vs_golden(adp, oracle_port, golden_dir, 
     e = rel_l2(out, torch.from_numpy(g["sample"]))
     print(f"ARVSampler 6 chunks x 4 steps: rel-L2 {e:.3e}")
     assert e <= 1e-2
+
+
+def close(got, want, what, rtol=1e-3, atol=1e-4):
+    """The fp32 criterion of the north star: |got - want| <= atol + rtol * |want| elementwise."""
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    err = (got - want).abs()
+    worst = float((err - rtol * want.abs()).max())
+    print(f"{what}: max abs err {float(err.max()):.3e}, rel-L2 {rel_l2(got, want):.3e}, "
+          f"max(err - rtol*|ref|) {worst:.3e} (atol {atol})")
+    torch.testing.assert_close(got, want, rtol=rtol, atol=atol)
+
+
+def test_fp32_verification_mode(adp, oracle_port, golden_dir):
+    """B200UNet.verify_fp32: the SAME launch program, weight packs and folds as the bf16 path with
+    fp32 storage and arithmetic (csrc/verify_f32.cu) meets rtol 1e-3 / atol 1e-4 against the
+    unmodified reference's golden vectors -- net, 5-step sampler, cross-attention + guidance 5.0,
+    the SkipCat (use_modulation=False) net -- and against the oracle on the 9-level README net."""
+    g = load(golden_dir, "tiny_unconditional.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**TINY)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    x, sigma = t(g["x"]), t(g["sigma"])
+    v_bf16 = model.net(x, sigma).clone()
+    model.net.verify_fp32 = True
+    for call in range(3):                   # eager, capture, replay
+        v = model.net(x, sigma)
+    close(v, torch.from_numpy(g["v"]), "fp32 mode: tiny net forward")
+    close(v - x, torch.from_numpy(g["v"]) - x.cpu(), "fp32 mode: tiny net branch (v - skip)")
+    close(model.sample(t(g["noise"]), num_steps=5), torch.from_numpy(g["sample5"]), "fp32 mode: VSampler 5 steps")
+    model.net.verify_fp32 = False           # and back: the tensor-core path is rebuilt
+    assert rel_l2(model.net(x, sigma), v_bf16) <= 1e-4
+
+    g = load(golden_dir, "tiny_text_cfg.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**TINY_TEXT)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **TINY_TEXT).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.net.verify_fp32 = True
+    x, sigma, emb = t(g["x"]), t(g["sigma"]), t(g["embedding"])
+    close(model.net(x, sigma, embedding=emb), torch.from_numpy(g["v_scale1"]), "fp32 mode: text-cond, scale 1")
+    close(model.net(x, sigma, embedding=emb, embedding_scale=5.0), torch.from_numpy(g["v_scale5"]),
+          "fp32 mode: text-cond, CFG 5")
+    close(model.sample(t(g["noise"]), num_steps=3, embedding=emb, embedding_scale=5.0),
+          torch.from_numpy(g["sample3"]), "fp32 mode: CFG sampler 3 steps")
+
+    g = load(golden_dir, "tiny_autoregressive.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionARPort(**TINY_AR)
+    model = adp.DiffusionAR(net_t=adp.UNetV0, **TINY_AR).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.net.verify_fp32 = True
+    gen = torch.Generator().manual_seed(int(g["input_seed"]))
+    audio = torch.randn(2, 2, 4096, generator=gen)
+    chan = torch.cat([audio, torch.rand(2, 1, 4096, generator=gen)], dim=1)
+    close(model.net(chan.to(DEV)), torch.from_numpy(g["v"]), "fp32 mode: SkipCat net")
+
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(**README)
+    model = adp.DiffusionModel(net_t=adp.UNetV0, **README).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.net.verify_fp32 = True
+    gen = torch.Generator().manual_seed(11)
+    x_small = torch.randn(2, 2, 2 ** 13, generator=gen)
+    sig = torch.rand(2, generator=gen)
+    v_ref = ref.net(x_small, sig)
+    v = model.net(x_small.to(DEV), sig.to(DEV))
+    close(v, v_ref, "fp32 mode: README 9-level net (2^13 clip)")
+    close(v.cpu() - x_small, v_ref - x_small, "fp32 mode: README net branch")
