@@ -35,6 +35,40 @@ def AppendChannelsPlugin(net_t: Callable, channels: int):
     return Net
 
 
+class _LearnedTransform(nn.Module):
+    """encode -> net -> decode; parameters registered in the reference's order (encode, decode, net)."""
+
+    def __init__(self, encode: nn.Module, decode: nn.Module, net: nn.Module):
+        super().__init__()
+        self.encode, self.decode, self.net = encode, decode, net
+
+    def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
+        return self.decode(self.net(self.encode(x), *args, **kwargs))
+
+
+def LTPlugin(net_t: Callable, num_filters: int, window_length: int, stride: int):
+    """Learned Transform plugin (reference components.py:113-157): a strided learned filterbank
+    (Conv1d, reflect padding, bias-free) in front of the net and its transposed counterpart behind
+    it; the net runs on `in_channels * num_filters` channels at 1/stride of the rate.  The two
+    filterbank convolutions are PyTorch modules around the net call; with the B200 U-Net inside, its
+    stem limits apply to the TRANSFORMED widths (in_channels * num_filters <= 8 inputs,
+    out_channels * num_filters <= 4 outputs) and are asserted by its constructor."""
+
+    def Net(dim: int, in_channels: int, out_channels: Optional[int] = None, **kwargs) -> nn.Module:
+        assert dim == 1, "the reference builds a ConvTranspose1d decoder: dim must be 1"
+        out_channels = default(out_channels, in_channels)
+        wide_in, wide_out = in_channels * num_filters, out_channels * num_filters
+        padding = window_length // 2 - stride // 2
+        encode = nn.Conv1d(in_channels, wide_in, kernel_size=window_length, stride=stride,
+                           padding=padding, padding_mode="reflect", bias=False)
+        decode = nn.ConvTranspose1d(wide_out, out_channels, kernel_size=window_length, stride=stride,
+                                    padding=padding, bias=False)
+        net = net_t(dim=dim, in_channels=wide_in, out_channels=wide_out, **kwargs)
+        return _LearnedTransform(encode, decode, net)
+
+    return Net
+
+
 class MelSpectrogram(nn.Module):
     """reference components.py:188-236 (DiffusionVocoder training front-end; runs once per
     call outside the step loop, torchaudio STFT + mel filterbank)."""

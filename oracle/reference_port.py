@@ -118,6 +118,24 @@ def build_unet_v0(dim: int, in_channels: int, channels: Sequence[int], factors: 
                  modulation_features=modulation_features, resnet_groups=resnet_groups)
 
 
+def lt_plugin(net_t: Callable, num_filters: int, window_length: int, stride: int) -> Callable:
+    """components.py:113-157 (LTPlugin): learned strided filterbank in front of / behind the net."""
+
+    def make(dim: int, in_channels: int, out_channels: Optional[int] = None, **kwargs) -> nn.Module:
+        out_channels = a_unet.default(out_channels, in_channels)                     # :121
+        wide_in, wide_out = in_channels * num_filters, out_channels * num_filters    # :122-123
+        padding = window_length // 2 - stride // 2                                   # :125
+        encode = nn.Conv1d(in_channels, wide_in, window_length, stride=stride, padding=padding,
+                           padding_mode="reflect", bias=False)                       # :126-135
+        decode = nn.ConvTranspose1d(wide_out, out_channels, window_length, stride=stride,
+                                    padding=padding, bias=False)                     # :136-143
+        net = net_t(dim=dim, in_channels=wide_in, out_channels=wide_out, **kwargs)   # :144-149
+        return a_unet.Module([encode, decode, net],
+                             lambda x, *a, **kw: decode(net(encode(x), *a, **kw)))    # :151-157
+
+    return make
+
+
 def append_channels_plugin(net_t: Callable, channels: int) -> Callable:
     """components.py:162-180 (AppendChannelsPlugin)."""
 

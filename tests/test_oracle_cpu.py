@@ -230,3 +230,29 @@ def test_package_sigma_ladder_matches_reference(golden_dir):
     lad = s.get_sigmas_ladder(num_items=2, num_steps_per_split=3)
     assert lad.shape == (4, 2, 1, 4096)
     assert torch.equal(lad[:, 0, 0], t(g["ladder3"])) and torch.equal(lad[:, 1, 0], t(g["ladder3"]))
+
+
+LT = dict(num_filters=4, window_length=8, stride=4)
+
+
+def test_oracle_learned_transform(oracle_port, golden_dir):
+    """tiny_learned_transform.npz: LTPlugin (reference components.py:113-157) around the net."""
+    g = load(golden_dir, "tiny_learned_transform.npz")
+    torch.manual_seed(0)
+    m = oracle_port.DiffusionModelPort(net_t=oracle_port.lt_plugin(oracle_port.build_unet_v0, **LT),
+                                       **dict(TINY, in_channels=1))
+    np.testing.assert_allclose(fingerprint(m), g["param_fingerprint"], rtol=1e-9)
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    x = torch.randn(2, 1, 16384, generator=gen)
+    sig = torch.rand(2, generator=gen)
+    with torch.no_grad():
+        assert rel_l2(m.net(x, sig), t(g["v"])) <= RTOL
+    torch.manual_seed(int(g["loss_seed"]))
+    loss = m(x)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    ps = list(m.net.parameters())
+    assert rel_l2(ps[0].grad, t(g["encode_grad"])) <= 10 * RTOL
+    assert rel_l2(ps[1].grad, t(g["decode_grad"])) <= 10 * RTOL
+    noise = torch.randn(2, 1, 16384, generator=gen)
+    assert rel_l2(m.sample(noise, num_steps=3), t(g["sample3"])) <= 10 * RTOL

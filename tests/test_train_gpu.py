@@ -435,3 +435,46 @@ def test_autoregressive_loss_and_gradients(oracle_port):
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
     assert worst < GRAD_TOL and cos > 1 - 1e-3
+
+
+def test_learned_transform_plugin(oracle_port):
+    """LTPlugin (reference components.py:113-157) around the B200 net: forward / 3-step sample
+    against the oracle and, through the differentiable net (the filterbanks are PyTorch modules on
+    both sides of it: d(input) of the hand-written backward feeds the encoder), the loss and every
+    gradient incl. the two filterbanks."""
+    import audio_diffusion_pytorch_b200 as adp
+    lt = dict(num_filters=4, window_length=8, stride=4)
+    cfg = dict(ATT, in_channels=1)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionModelPort(net_t=oracle_port.lt_plugin(oracle_port.build_unet_v0, **lt), **cfg)
+    model = adp.DiffusionModel(net_t=adp.LTPlugin(adp.UNetV0, **lt), **cfg).to(DEV)
+    with torch.no_grad():
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert p.shape == q.shape
+            p.copy_(q)
+    g = torch.Generator().manual_seed(26)
+    x = torch.randn(2, 1, 16384, generator=g)
+    sig = torch.rand(2, generator=g)
+    noise = torch.randn(2, 1, 16384, generator=g)
+    with torch.no_grad():
+        v, v_ref = model.net(x.to(DEV), sig.to(DEV)), ref.net(x, sig)
+        e = float((v.cpu() - v_ref).norm() / v_ref.norm())
+        s, s_ref = model.sample(noise.to(DEV), num_steps=3), ref.sample(noise, num_steps=3)
+        e_s = float((s.cpu() - s_ref).norm() / s_ref.norm())
+    print(f"LTPlugin forward rel-L2 {e:.3e}, 3-step sample rel-L2 {e_s:.3e}")
+    assert e <= 5e-3 and e_s <= 5e-3
+    for call in range(3):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(93)
+        loss = model(x.to(DEV))
+        loss.backward()
+    torch.manual_seed(93)
+    sigma = torch.rand(2, device=DEV).cpu()
+    eps = torch.randn(2, 1, 16384, device=DEV).cpu()
+    loss_ref = oracle_loss(ref.net, x, eps, sigma)
+    loss_ref.backward()
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"LTPlugin loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
+    assert rel < 2e-3
+    worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
+    assert worst < GRAD_TOL and cos > 1 - 1e-3
