@@ -189,3 +189,35 @@ def test_upsampler_and_vocoder_conditioning_paths(oracle_port):
     assert torch.equal(guide, vref.to_flat(mel.reshape(-1, 8, 256)))
     audio = torch.randn(2, 2, 4096)
     assert torch.allclose(voc.to_spectrogram(audio), vref.to_spectrogram(audio), atol=1e-6)
+
+
+def test_skipcat_packs_reproduce_the_merge():
+    """Host side of the use_modulation=False (SkipCat) path: the 1x1 merge conv folded into the
+    level-0 stem weights, and the block-diagonal (two positions per row) packs of an 8-channel
+    level, both reproduce conv1x1(cat([skip * 2^-0.5, y])) in fp32."""
+    import audio_diffusion_pytorch_b200 as adp
+    torch.manual_seed(3)
+    net = adp.UNetV0(dim=1, in_channels=3, out_channels=2, channels=[8, 32], factors=[1, 4], items=[1, 1],
+                     use_modulation=False, use_time_conditioning=False)
+    with ops_pack_fp32():
+        P = net._compute_packed_impl()
+    lv0, lv1 = net.levels()
+    L0, L1 = P["levels"]
+    x, h = torch.randn(2, 3, 64), torch.randn(2, 8, 64)
+    with torch.no_grad():
+        want = lv0.merge(torch.cat([lv0.adapter(x) * 2 ** -0.5, lv0.up(h)], dim=1))
+    got = F.conv1d(x, L0["adapt_w"][:, :, None], L0["adapt_b"]) + F.conv1d(h, L0["up_w"], L0["up_b"], padding=1)
+    assert float((got - want).abs().max()) <= 1e-5
+    # level 1: out = Wc1 (skip * s) + Wc2 y + bc on [B, T/2, 16] views of 8-channel tensors
+    skip, y = torch.randn(2, 64, 8), torch.randn(2, 64, 8)
+    with torch.no_grad():
+        want = lv1.merge(torch.cat([skip.transpose(1, 2) * 2 ** -0.5, y.transpose(1, 2)], dim=1)).transpose(1, 2)
+    w1, w2 = L1["cat_w1"].float(), L1["cat_w2"].float()
+    assert w1.shape == (16, 16)
+    got = (skip.reshape(2, 32, 16) @ w1.t() + L1["cat_b"] + y.reshape(2, 32, 16) @ w2.t()).reshape(2, 64, 8)
+    assert float((got - want).abs().max()) <= 1e-5
+
+
+def ops_pack_fp32():
+    from audio_diffusion_pytorch_b200 import ops
+    return ops.pack_dtype(torch.float32)
