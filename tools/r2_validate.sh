@@ -20,6 +20,8 @@ for c in ("cfg2", "cfg3", "cfg5"):
     except Exception as e:
         print(c, "ERR", e)
 PY
-for c in cfg2 cfg3 cfg5; do python tools/graph_profile.py $c 3 0 2>/dev/null > gpurun_out/graph_$c.txt; done
-bash tools/ncu_capture.sh mid_conv r2_ncu_mid_conv64 mid 8 16384 64
-bash tools/ncu_capture.sh mid_conv r2_ncu_mid_conv32 mid 8 65536 32
+if [ "$1" = "full" ]; then     # per-shape tables and ncu captures of the thin-level kernels
+  for c in cfg2 cfg3 cfg5; do python tools/graph_profile.py $c 3 0 2>/dev/null > gpurun_out/graph_$c.txt; done
+  bash tools/ncu_capture.sh mid_conv r2_ncu_mid_conv64 mid 8 16384 64
+  bash tools/ncu_capture.sh mid_conv r2_ncu_mid_conv32 mid 8 65536 32
+fi
