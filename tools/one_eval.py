@@ -16,7 +16,8 @@ model = adp.DiffusionModel(net_t=adp.UNetV0, **README).cuda()
 model.net.use_cuda_graph = False
 x = torch.randn(batch, 2, 2 ** 18, device="cuda")
 sig = torch.full((batch,), 0.5, device="cuda")
-for _ in range(evals):
-    v = model.net(x, sig)
+with torch.no_grad():          # the inference plan (with autograd recording, net() is the training forward)
+    for _ in range(evals):
+        v = model.net(x, sig)
 torch.cuda.synchronize()
 print("done", float(v.abs().mean()))
