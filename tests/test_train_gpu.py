@@ -72,8 +72,8 @@ def test_loss_and_gradients_match_oracle(oracle_port, upsampler):
         model.zero_grad(set_to_none=True)
         loss = fused_v_loss(model.net, x.to(DEV), noise.to(DEV), sigma.to(DEV), **extra)
         loss.backward()
-        rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-        print(f"call {call}: loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+        rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+        print(f"call {call}: loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
         assert rel < 2e-3
         worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
         assert worst < GRAD_TOL and cos > 1 - 1e-3
@@ -101,7 +101,7 @@ def test_optimizer_step_refreshes_packed_weights(oracle_port):
         loss.backward(); opt.step()
         lr_ = oracle_loss(ref.net, x, noise, sigma)
         lr_.backward(); opt_ref.step()
-        losses.append(float(loss)); losses_ref.append(float(lr_))
+        losses.append(float(loss.detach())); losses_ref.append(float(lr_.detach()))
     print("losses", losses, "oracle", losses_ref)
     for a, b in zip(losses, losses_ref):
         assert abs(a - b) / b < 5e-3
@@ -153,8 +153,8 @@ def test_attention_gradients_match_oracle(oracle_port, case):
         model.zero_grad(set_to_none=True)
         loss = fused_v_loss(model.net, x.to(DEV), noise.to(DEV), sigma.to(DEV), **kw)
         loss.backward()
-        rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-        print(f"{case} call {call}: loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+        rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+        print(f"{case} call {call}: loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
         assert rel < 2e-3
         ref_named = [(n, p) for n, p in ref.net.named_parameters() if p.grad is not None]
         got = [q for (n, p), q in zip(ref.net.named_parameters(), model.net.parameters()) if p.grad is not None]
@@ -187,8 +187,8 @@ def test_custom_loss_through_differentiable_forward(oracle_port, cfg_name):
     b = torch.sin(sigma * math.pi / 2)[:, None, None]
     loss_ref = F.l1_loss(ref.net(a * x + b * noise, sigma), a * noise - b * x)
     loss_ref.backward()
-    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-    print(f"l1 loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"l1 loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
     # d|e|/de = sign(e): elements whose bf16 error flips the sign contribute O(1) changes
@@ -244,8 +244,8 @@ def test_vocoder_forward_trains_to_flat(oracle_port):
     rows = audio.reshape(-1, 1, audio.shape[-1])
     loss_ref = oracle_loss(ref.net, rows, noise, sigma, append_channels=guide)
     loss_ref.backward()
-    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-    print(f"vocoder loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"vocoder loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     got, want = model.to_flat.weight.grad, ref.to_flat.weight.grad
     assert got is not None, "to_flat.weight received no gradient"
@@ -343,8 +343,8 @@ def test_nine_level_gradients(oracle_port):
     loss_ref.backward()
     loss = fused_v_loss(model.net, x.to(DEV), noise.to(DEV), sigma.to(DEV), append_channels=app.to(DEV))
     loss.backward()
-    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-    print(f"9-level loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"9-level loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
     assert worst < 0.1 and cos > 1 - 2e-3
@@ -393,8 +393,8 @@ def test_autoencoder_trains_encoder_through_injected_context(oracle_port):
     latent = ref.encoder(audio)
     loss_ref = oracle_loss(ref.net, audio, noise, sigma, channels=[None, None, latent])
     loss_ref.backward()
-    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-    print(f"autoencoder loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"autoencoder loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
     assert worst < GRAD_TOL and cos > 1 - 1e-3
@@ -430,8 +430,8 @@ def test_autoregressive_loss_and_gradients(oracle_port):
     a, b = torch.cos(sig * math.pi / 2), torch.sin(sig * math.pi / 2)
     loss_ref = F.mse_loss(ref.net(torch.cat([a * audio + b * noise, sig], dim=1)), a * noise - b * audio)
     loss_ref.backward()
-    rel = abs(float(loss) - float(loss_ref)) / float(loss_ref)
-    print(f"DiffusionAR loss {float(loss):.6f} vs oracle {float(loss_ref):.6f} (rel {rel:.2e})")
+    rel = abs(float(loss.detach()) - float(loss_ref.detach())) / float(loss_ref.detach())
+    print(f"DiffusionAR loss {float(loss.detach()):.6f} vs oracle {float(loss_ref.detach()):.6f} (rel {rel:.2e})")
     assert rel < 2e-3
     worst, cos = compare_grads(list(ref.net.named_parameters()), list(model.net.parameters()))
     assert worst < GRAD_TOL and cos > 1 - 1e-3
