@@ -440,3 +440,43 @@ def test_fp32_verification_mode(adp, oracle_port, golden_dir):
     v = model.net(x_small.to(DEV), sig.to(DEV))
     close(v, v_ref, "fp32 mode: README 9-level net (2^13 clip)")
     close(v.cpu() - x_small, v_ref - x_small, "fp32 mode: README net branch")
+
+
+def test_fp32_verification_mode_model_wrappers(adp, oracle_port, golden_dir):
+    """verify_fp32 through the model wrappers: appended channels (Upsampler, Vocoder) and the
+    injected latent (DiffusionAE) take the fp32 stem / GEMM kernels; 3-step samples against the
+    unmodified reference's vectors at rtol 1e-3 / atol 1e-4."""
+    g = load(golden_dir, "tiny_upsampler.npz")
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionUpsamplerPort(upsample_factor=16, in_channels=2, **TINY_NOATT)
+    model = adp.DiffusionUpsampler(net_t=adp.UNetV0, upsample_factor=16, in_channels=2, **TINY_NOATT).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.net.verify_fp32 = True
+    s = model.sample(t(g["low"]), num_steps=3, generator=torch.Generator().manual_seed(5))
+    close(s, torch.from_numpy(g["sample3"]), "fp32 mode: DiffusionUpsampler.sample")
+
+    g = load(golden_dir, "tiny_vocoder.npz")
+    kw = dict(mel_n_fft=64, mel_channels=8, mel_sample_rate=48000, mel_normalize_log=True, **TINY_NOATT)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionVocoderPort(**kw)
+    model = adp.DiffusionVocoder(net_t=adp.UNetV0, **kw).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.to_flat.load_state_dict(ref.to_flat.state_dict())
+    model.net.verify_fp32 = True
+    s = model.sample(t(g["mel"]), num_steps=3, generator=torch.Generator().manual_seed(8))
+    close(s, torch.from_numpy(g["sample3"]), "fp32 mode: DiffusionVocoder.sample")
+
+    g = load(golden_dir, "tiny_autoencoder.npz")
+    cfg = dict(TINY, inject_depth=2)
+    torch.manual_seed(0)
+    ref = oracle_port.DiffusionAEPort(encoder=oracle_port.ToyEncoder(), **cfg)
+    torch.manual_seed(0)
+    model = adp.DiffusionAE(encoder=oracle_port.ToyEncoder(), net_t=adp.UNetV0, **cfg).to(DEV)
+    model.net.load_reference_parameters(ref.net)
+    model.encoder.load_state_dict(ref.encoder.state_dict())
+    model.net.verify_fp32 = True
+    audio = torch.randn(2, 2, 4096, generator=torch.Generator().manual_seed(int(g["audio_seed"])))
+    latent = model.encode(audio.to(DEV))
+    noise = torch.randn((2, 2, 4096), generator=torch.Generator().manual_seed(int(g["decode_seed"])))
+    out = model.sampler(noise.to(DEV), num_steps=3, channels=[None, None, latent])
+    close(out, torch.from_numpy(g["decode3"]), "fp32 mode: DiffusionAE decode")
