@@ -221,3 +221,26 @@ def test_skipcat_packs_reproduce_the_merge():
 def ops_pack_fp32():
     from audio_diffusion_pytorch_b200 import ops
     return ops.pack_dtype(torch.float32)
+
+
+def test_arv_diffusion_algebra_and_rng_order(oracle_port):
+    """ARVDiffusion (reference diffusion.py:98-130) around an arbitrary net, on the host: the
+    product class draws rand((B,1,n)) then randn_like(x) and forms the same noised input, sigma
+    channel and target as the oracle port (bit-identical with a pointwise toy net)."""
+    from audio_diffusion_pytorch_b200.diffusion import ARVDiffusion
+
+    class Toy(torch.nn.Module):
+        def forward(self, chan, **kw):
+            return torch.tanh(chan[:, :2]) * (1.0 + chan[:, 2:3])
+
+    x = torch.randn(3, 2, 64, generator=torch.Generator().manual_seed(4))
+    ours, theirs = ARVDiffusion(net=Toy(), length=64, num_splits=4), oracle_port.ARVDiffusionPort(Toy(), 64, 4)
+    torch.manual_seed(11)
+    a = ours(x)
+    torch.manual_seed(11)
+    b = theirs(x)
+    assert torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        ours(x[..., :32])                       # input length must match `length`
+    with pytest.raises(AssertionError):
+        ARVDiffusion(net=Toy(), length=64, num_splits=5)
