@@ -811,7 +811,14 @@ static int dispatch_bn2(const adp_conv_gemm_args& a, int bn, cudaStream_t s) {
 
 }  // namespace adp
 
+namespace adp { extern int g_mid_threads; }
+
 extern "C" int adp_debug_set(int key, int value) {
+  if (key == 8) {            // threads per block of the thin-level ConvBlock kernels (128 or 256)
+    if (value != 128 && value != 256) return adp::set_error("adp_debug_set: key 8 takes 128 or 256");
+    adp::g_mid_threads = value;
+    return 0;
+  }
   if (key < 0 || key >= 8) return adp::set_error("adp_debug_set: bad key %d", key);
   adp::g_debug[key] = value;
   if (key == 6) adp::g_pdl = value;

@@ -33,17 +33,21 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int C>
+// NTH = threads per block.  256 threads x 2 blocks / SM or 128 threads x 4 blocks / SM (half-size
+// tiles): the same 16 warps per SM, but four independent barrier-separated phase streams instead
+// of two (selected by g_mid_threads, adp_debug_set(8, ..)).
+template <int C, int NTH>
 struct MidCfg {
-  static constexpr int TB = C == 32 ? 256 : 128;       // rows per tile
-  static constexpr int TPR = 256 / TB;                 // staging threads per row
+  static constexpr int TB = (C == 32 ? 256 : 128) * NTH / 256;  // rows per tile
+  static constexpr int TPR = NTH / TB;                 // staging threads per row
+  static constexpr int RPW = TB / (NTH / 32);          // rows per warp in the MMA phase
   static constexpr int RS = C * 2 + 16;                // padded smem row stride of s_x (bytes)
   static constexpr int WS = 3 * C * 2 + 16;            // padded stride of one W row (n) in smem
-  static constexpr int MB = TB / 8 / 16;               // m16 blocks per warp
+  static constexpr int MB = RPW / 16;                  // m16 blocks per warp
   static constexpr int NT = C / 8;                     // n8 tiles
   static constexpr int OS = C + 4;                     // padded fp32 row stride of s_o (floats)
   static constexpr int LPR = C / 8;                    // epilogue lanes per row (8 channels each)
-  static constexpr int ER = TB * LPR / 256;            // epilogue rows per thread
+  static constexpr int ER = TB * LPR / NTH;            // epilogue rows per thread
   static constexpr int X_BYTES = (TB + 2) * RS;
   static constexpr int O_BYTES = TB * OS * 4;
   static constexpr int W_BYTES = C * WS;
@@ -59,11 +63,11 @@ struct MidCfg {
 // reduction.  (The first version ran the epilogue in the accumulator-fragment layout: 4-byte
 // stores, 4-byte shared-memory residual reads and a shuffle chain per fragment row made the
 // kernel issue/latency bound at 15-40 % of HBM bandwidth, profiles/r2_ncu_mid_conv64.txt.)
-template <int C>
-__global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_args a) {
-  using Cfg = MidCfg<C>;
+template <int C, int NTH>
+__global__ void __launch_bounds__(NTH, 512 / NTH) mid_conv_kernel(const adp_narrow_conv_args a) {
+  using Cfg = MidCfg<C, NTH>;
   constexpr int TB = Cfg::TB, TPR = Cfg::TPR, RS = Cfg::RS, WS = Cfg::WS, MB = Cfg::MB, NT = Cfg::NT;
-  constexpr int OS = Cfg::OS, LPR = Cfg::LPR, ER = Cfg::ER;
+  constexpr int OS = Cfg::OS, LPR = Cfg::LPR, ER = Cfg::ER, RPW = Cfg::RPW;
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
@@ -84,12 +88,12 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
   if (a.w_packed) {            // bf16 [C][3C] image prepared by the host: straight 16-byte copy
     constexpr int VPRW = 3 * C * 2 / 16;             // 16-byte vectors per W row
     const uint4* wp = static_cast<const uint4*>(a.w_packed);
-    for (int i = tid; i < C * VPRW; i += 256) {
+    for (int i = tid; i < C * VPRW; i += NTH) {
       const int co = i / VPRW, v = i - co * VPRW;
       *reinterpret_cast<uint4*>(s_w + co * WS + v * 16) = __ldg(wp + i);
     }
   } else {                     // PyTorch fp32 [co][ci][tap] -> [co][tap*C + ci]
-    for (int pidx = tid; pidx < C * C; pidx += 256) {
+    for (int pidx = tid; pidx < C * C; pidx += NTH) {
       const int co = pidx / C, ci = pidx % C;
       const float* src = a.w + static_cast<size_t>(pidx) * 3;
 #pragma unroll
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
     if (has_res) {
 #pragma unroll
       for (int i = 0; i < ER; ++i) {
-        const int t = t0 + erow0 + i * (256 / LPR);
+        const int t = t0 + erow0 + i * (NTH / LPR);
         res[i] = make_uint4(0, 0, 0, 0);
         if (t < a.T) res[i] = __ldg(reinterpret_cast<const uint4*>(rb + static_cast<size_t>(t) * C + el * 8));
       }
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
         uint32_t af[MB][4];
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
-          const int r0 = warp * (TB / 8) + mb * 16;
+          const int r0 = warp * RPW + mb * 16;
           // matrices: (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
           ldsm_x4(x_base + static_cast<uint32_t>(r0 + (lane & 7) + ((lane >> 3) & 1) * 8 + tap) * RS +
                       (c16 * 16 + ((lane >> 4) & 1) * 8) * 2, af[mb]);
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
     // accumulator fragments -> row-major fp32 tile: lane (g, q) owns rows g / g+8, channels 8j+2q, +1
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) {
-      const int r = warp * (TB / 8) + mb * 16 + g;
+      const int r = warp * RPW + mb * 16 + g;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         *reinterpret_cast<float2*>(s_o + r * OS + 8 * j + 2 * q) = make_float2(acc[mb][j][0], acc[mb][j][1]);
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
     // row-wise epilogue: this thread's 8 channels of ER rows
 #pragma unroll
     for (int i = 0; i < ER; ++i) {
-      const int rl = erow0 + i * (256 / LPR);
+      const int rl = erow0 + i * (NTH / LPR);
       const int t = t0 + rl;
       const float4 o0 = *reinterpret_cast<const float4*>(s_o + rl * OS + el * 8);
       const float4 o1 = *reinterpret_cast<const float4*>(s_o + rl * OS + el * 8 + 4);
@@ -315,28 +319,33 @@ __global__ void __launch_bounds__(256, 2) mid_conv_kernel(const adp_narrow_conv_
   }
 }
 
-template <int C>
+// 256: measured A/B on B200 (tools/time_mid_threads.py, L2 flushed): 128 x 4 is 5-6 % faster for
+// C = 32 at 16 batch rows, 7-8 % slower for C = 64 at 8, equal elsewhere; no change end to end
+int g_mid_threads = 256;
+
+template <int C, int NTH>
 static int launch_mid(const adp_narrow_conv_args& a, cudaStream_t stream) {
-  using Cfg = MidCfg<C>;
+  using Cfg = MidCfg<C, NTH>;
   static SmemAttrCache smem_cache;
-  ADP_CUDA(ensure_dyn_smem(mid_conv_kernel<C>, (size_t)Cfg::SMEM, smem_cache));
+  ADP_CUDA(ensure_dyn_smem(mid_conv_kernel<C, NTH>, (size_t)Cfg::SMEM, smem_cache));
   int dev = 0, sms = 148, occ = 1;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mid_conv_kernel<C>, 256, Cfg::SMEM) != cudaSuccess ||
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mid_conv_kernel<C, NTH>, NTH, Cfg::SMEM) != cudaSuccess ||
       occ < 1)
     occ = 1;
   const int n_tiles = (a.T + Cfg::TB - 1) / Cfg::TB;
   int gx = (occ * sms) / a.B;               // one wave of persistent blocks
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
-  ADP_CUDA(launch_k(mid_conv_kernel<C>, dim3(gx, a.B), dim3(256), (size_t)Cfg::SMEM, stream, a));
+  ADP_CUDA(launch_k(mid_conv_kernel<C, NTH>, dim3(gx, a.B), dim3(NTH), (size_t)Cfg::SMEM, stream, a));
   return 0;
 }
 
 int mid_conv(const adp_narrow_conv_args& a, cudaStream_t stream) {
-  if (a.C == 32) return launch_mid<32>(a, stream);
-  if (a.C == 64) return launch_mid<64>(a, stream);
+  const bool small = g_mid_threads == 128;
+  if (a.C == 32) return small ? launch_mid<32, 128>(a, stream) : launch_mid<32, 256>(a, stream);
+  if (a.C == 64) return small ? launch_mid<64, 128>(a, stream) : launch_mid<64, 256>(a, stream);
   return set_error("adp_narrow_conv: C=%d is not built (8, 32, 64)", a.C);
 }
 
