@@ -244,3 +244,35 @@ def test_arv_diffusion_algebra_and_rng_order(oracle_port):
         ours(x[..., :32])                       # input length must match `length`
     with pytest.raises(AssertionError):
         ARVDiffusion(net=Toy(), length=64, num_splits=5)
+
+
+@pytest.mark.parametrize("n_fft,n_mels,sr", [(1024, 80, 48000), (256, 16, 16000), (2048, 128, 44100), (64, 8, 48000)])
+def test_mel_filter_bands_cover_every_nonzero(n_fft, n_mels, sr):
+    """Host tables of adp_mel_spectrogram: every mel filter's non-zero bins lie inside the
+    [lo, hi) range handed to the kernel (so the banded product equals the full matmul), the window
+    is padded to n_fft the way torch.stft centres it, and empty filters get an empty range."""
+    from audio_diffusion_pytorch_b200.components import MelSpectrogram
+    front = MelSpectrogram(n_fft=n_fft, hop_length=n_fft // 4, win_length=n_fft // 2, sample_rate=sr,
+                           n_mel_channels=n_mels)
+    window, fb, band = front._kernel_tables(torch.device("cpu"))
+    assert window.shape == (n_fft,) and fb.shape == (n_fft // 2 + 1, n_mels) and band.shape == (n_mels, 2)
+    quarter = n_fft // 4
+    assert torch.equal(window[quarter:quarter + n_fft // 2], front.to_spectrogram.window)
+    assert float(window[:quarter].abs().sum() + window[quarter + n_fft // 2:].abs().sum()) == 0.0
+    mag = torch.rand(n_fft // 2 + 1)
+    full = mag @ fb
+    banded = torch.stack([(mag[lo:hi] * fb[lo:hi, m]).sum() for m, (lo, hi) in enumerate(band.tolist())])
+    assert torch.allclose(banded, full, rtol=1e-6, atol=1e-7)
+    for m, (lo, hi) in enumerate(band.tolist()):
+        assert 0 <= lo <= hi <= n_fft // 2 + 1
+        if not bool((fb[:, m] != 0).any()):
+            assert lo == hi
+
+
+@pytest.mark.parametrize("fi,fo", [(1, 16), (16, 1), (3, 2), (4, 1)])
+def test_polyphase_bank_geometry(fi, fo):
+    """adp_resample's contract with the host filter bank: [factor_out, taps] with
+    taps = 2*half + factor_in."""
+    from audio_diffusion_pytorch_b200.utils import _polyphase_bank
+    bank, half = _polyphase_bank(fi, fo, 0.99, 6, torch.float32, "cpu")
+    assert bank.shape == (fo, 1, 2 * half + fi)
